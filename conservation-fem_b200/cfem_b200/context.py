@@ -1,0 +1,251 @@
+"""Host-side handle on one mesh: owns the C-ABI context and exposes the hot-path
+operators with numpy / torch arrays in the caller's (dolfinx) numbering.
+
+PyTorch is never required here; CUDA tensors are accepted as arguments (their
+``data_ptr()`` is passed through) because the north star allows torch as the
+buffer allocator.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib as L
+from .meshes import as_mesh
+
+
+def _field(a):
+    """Accept a dolfinx-like Function (``.x.array``), numpy array or torch tensor."""
+    if a is None:
+        return None
+    if hasattr(a, "x") and hasattr(a.x, "array"):
+        a = a.x.array
+    return L.f64(a)
+
+
+class Context:
+    """Everything the reference recomputes per step but that depends only on the mesh.
+
+    Built once from a dolfinx mesh or an ``(x, cells)`` pair: Hilbert ordering,
+    node patches / CSR pattern (``Code/Utils/SI.py:12-28``), boundary dofs
+    (``Code/KPP/KPP_exact.py:85-89``), mass matrices, assembly tiles.
+    """
+
+    _cache: "weakref.WeakValueDictionary" = weakref.WeakValueDictionary()
+
+    def __init__(self, domain, device=0, order="hilbert"):
+        lib = L.load()
+        x, cells = as_mesh(domain)
+        self.x = x
+        self.cells = cells
+        self.n = x.shape[0]
+        h = C.c_void_p()
+        L.check(lib.cfem_create(C.byref(h), int(device), x.shape[0], cells.shape[0], L.ptr(x), 2,
+                                L.ptr(cells), 4, L.ORDER_HILBERT if order == "hilbert" else L.ORDER_NATURAL))
+        self._h = h
+        self._lib = lib
+        self.nnz = lib.cfem_num_nonzeros(h)
+        self._pattern = None
+        self._h_nodal = None
+
+    # -- life cycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cfem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @classmethod
+    def for_domain(cls, domain, **kw):
+        """One cached context per mesh object (RV / SI / get_nodal_h share it)."""
+        key = id(domain)
+        ctx = cls._cache.get(key)
+        if ctx is None or ctx._h is None:
+            ctx = cls(domain, **kw)
+            try:
+                cls._cache[key] = ctx
+                ctx._owner = weakref.ref(domain) if not isinstance(domain, (tuple, list)) else None
+            except TypeError:
+                pass
+        return ctx
+
+    # -- mesh relations
+    @property
+    def num_tiles(self):
+        return self._lib.cfem_num_tiles(self._h)
+
+    @property
+    def device_bytes(self):
+        return self._lib.cfem_device_bytes(self._h)
+
+    def csr_pattern(self):
+        if self._pattern is None:
+            rowptr = np.empty(self.n + 1, dtype=np.int32)
+            colidx = np.empty(self.nnz, dtype=np.int32)
+            L.check(self._lib.cfem_get_csr_pattern(self._h, L.ptr(rowptr), L.ptr(colidx)))
+            self._pattern = (rowptr, colidx)
+        return self._pattern
+
+    def patch_dictionary(self):
+        """dict node -> set(nodes) like ``SI.get_patch_dictionary`` (keys ascending)."""
+        rowptr, colidx = self.csr_pattern()
+        return {int(i): set(colidx[rowptr[i]:rowptr[i + 1]].tolist()) for i in range(self.n)}
+
+    def boundary_dofs(self):
+        nb = self._lib.cfem_num_boundary(self._h)
+        out = np.empty(nb, dtype=np.int32)
+        L.check(self._lib.cfem_get_boundary_dofs(self._h, L.ptr(out)))
+        return out
+
+    def set_dirichlet(self, dofs):
+        dofs = np.ascontiguousarray(dofs, dtype=np.int32)
+        L.check(self._lib.cfem_set_dirichlet(self._h, L.ptr(dofs), dofs.size))
+
+    def ordering(self):
+        out = np.empty(self.n, dtype=np.int32)
+        L.check(self._lib.cfem_get_ordering(self._h, L.ptr(out)))
+        return out
+
+    # -- (a-1)
+    def nodal_h(self, rtol=1e-14, max_it=1000):
+        if self._h_nodal is None:
+            out = np.empty(self.n)
+            it = C.c_int(0)
+            L.check(self._lib.cfem_nodal_h(self._h, L.ptr(out), rtol, max_it, C.byref(it)))
+            self._h_nodal = out
+            self.nodal_h_iterations = it.value
+        return self._h_nodal.copy()
+
+    # -- (a-3)
+    def rv_residual(self, flux, scheme, dt, u_n, u_old, u_oo=None, w=None, use_bc=True, R0=None,
+                    rtol=1e-13, max_it=1000):
+        R = np.zeros(self.n) if R0 is None else np.array(_field(R0), dtype=np.float64, copy=True)
+        it = C.c_int(0)
+        u_n, u_old, u_oo, w = _field(u_n), _field(u_old), _field(u_oo), _field(w)
+        L.check(self._lib.cfem_rv_residual(self._h, _flux(flux), L.BDF2 if scheme in ("bdf2", 2) else L.BDF1,
+                                           float(dt), L.ptr(u_n), L.ptr(u_old), L.ptr(u_oo), L.ptr(w),
+                                           int(bool(use_bc)), L.ptr(R), rtol, max_it, C.byref(it)))
+        self.last_iterations = it.value
+        return R
+
+    # -- (a-4..6)
+    def rv_epsilon(self, variant, flux, Cvel, Crv, uh=None, u_n=None, Rh=None, h=None, w=None, out=None):
+        variant = {"nonlinear": L.EPS_NONLINEAR, "linear": L.EPS_LINEAR, "pointwise": L.EPS_POINTWISE,
+                   "first_order": L.EPS_FIRST_ORDER, "linear_simple": L.EPS_LINEAR_SIMPLE}.get(variant, variant)
+        eps = np.empty(self.n) if out is None else out
+        uh, u_n, Rh, h, w = _field(uh), _field(u_n), _field(Rh), _field(h), _field(w)
+        L.check(self._lib.cfem_rv_epsilon(self._h, variant, _flux(flux), float(Cvel), float(Crv), L.ptr(uh),
+                                          L.ptr(u_n), L.ptr(Rh), L.ptr(h), L.ptr(w), L.ptr(eps)))
+        return eps
+
+    # -- (a-7, a-8)
+    def assemble_advection(self, dt, w, eps, u_n, bc_values=None):
+        b = np.empty(self.n)
+        w, eps, u_n, bc_values = _field(w), _field(eps), _field(u_n), _field(bc_values)
+        L.check(self._lib.cfem_assemble_advection(self._h, float(dt), L.ptr(w), L.ptr(eps), L.ptr(u_n),
+                                                  L.ptr(bc_values), L.ptr(b)))
+        return b
+
+    def assemble_cn_residual(self, flux, dt, uh, u_n, eps, bc_values=None):
+        F = np.empty(self.n)
+        uh, u_n, eps, bc_values = _field(uh), _field(u_n), _field(eps), _field(bc_values)
+        L.check(self._lib.cfem_assemble_cn_residual(self._h, _flux(flux), float(dt), L.ptr(uh), L.ptr(u_n),
+                                                    L.ptr(eps), L.ptr(bc_values), L.ptr(F)))
+        return F
+
+    def assemble_cn_jacobian(self, flux, dt, uh, eps):
+        uh, eps = _field(uh), _field(eps)
+        L.check(self._lib.cfem_assemble_cn_jacobian(self._h, _flux(flux), float(dt), L.ptr(uh), L.ptr(eps)))
+
+    def assemble_stiffness(self, eps=None):
+        eps = _field(eps)
+        L.check(self._lib.cfem_assemble_stiffness(self._h, L.ptr(eps)))
+
+    def matrix(self, which):
+        """Context matrix as a scipy CSR in caller numbering."""
+        import scipy.sparse as sp
+
+        rowptr, colidx = self.csr_pattern()
+        vals = np.empty(self.nnz)
+        L.check(self._lib.cfem_matrix_values(self._h, int(which), L.ptr(vals)))
+        return sp.csr_matrix((vals, colidx.copy(), rowptr.copy()), shape=(self.n, self.n))
+
+    # -- (a-9)
+    def spmv(self, which, x):
+        x = _field(x)
+        y = np.empty(self.n)
+        L.check(self._lib.cfem_spmv(self._h, int(which), L.ptr(x), L.ptr(y)))
+        return y
+
+    def solve(self, which, b, x0=None, solver="pcg", rtol=1e-13, atol=0.0, max_it=2000):
+        b = _field(b)
+        x = np.zeros(self.n) if x0 is None else np.array(_field(x0), dtype=np.float64, copy=True)
+        it, rr = C.c_int(0), C.c_double(0.0)
+        L.check(self._lib.cfem_solve(self._h, int(which), L.SOLVER_BY_NAME.get(solver, solver), L.ptr(b), L.ptr(x),
+                                     rtol, atol, max_it, C.byref(it), C.byref(rr)))
+        self.last_iterations, self.last_relres = it.value, rr.value
+        return x
+
+    # -- (a-10)
+    def state_set(self, uh=None, u_n=None, u_old=None, u_oo=None, RH=None, h=None, w=None, t=0.0):
+        args = [_field(a) for a in (uh, u_n, u_old, u_oo, RH, h, w)]
+        self._keep = args
+        L.check(self._lib.cfem_state_set(self._h, *[L.ptr(a) for a in args], float(t)))
+
+    def state_get(self, names=("uh",), out=None):
+        """Return dict name -> array for names among uh,u_n,u_old,u_oo,RH,eps (+ 't')."""
+        order = ("uh", "u_n", "u_old", "u_oo", "RH", "eps")
+        bufs = {k: ((out or {}).get(k) if out and k in out else np.empty(self.n)) for k in names if k in order}
+        t = C.c_double(0.0)
+        L.check(self._lib.cfem_state_get(self._h, *[L.ptr(bufs.get(k)) for k in order], C.byref(t)))
+        bufs["t"] = t.value
+        return bufs
+
+    def step_scalar(self, params: "L.StepParams", n_steps=1, bc_values=None):
+        st = L.StepStats()
+        bc_values = _field(bc_values)
+        L.check(self._lib.cfem_step_scalar(self._h, C.byref(params), int(n_steps), L.ptr(bc_values), C.byref(st)))
+        return st.as_dict()
+
+    def step_advection(self, params: "L.StepParams", n_steps=1, first_gfem=False):
+        st = L.StepStats()
+        L.check(self._lib.cfem_step_advection(self._h, C.byref(params), int(n_steps), int(bool(first_gfem)),
+                                              C.byref(st)))
+        return st.as_dict()
+
+    def time_kernel(self, kernel, flux, reps=20):
+        ms, by = C.c_double(0.0), C.c_double(0.0)
+        L.check(self._lib.cfem_time_kernel(self._h, int(kernel), _flux(flux), int(reps), C.byref(ms), C.byref(by)))
+        return ms.value, by.value
+
+    def synchronize(self):
+        L.check(self._lib.cfem_synchronize(self._h))
+
+
+def _flux(flux):
+    if isinstance(flux, str):
+        return L.FLUX_BY_NAME[flux]
+    return int(flux)
+
+
+def step_params(flux, dt, Cvel, Crv, scheme="bdf2", newton_rtol=1e-4, newton_atol=1e-10, newton_max_it=100,
+                solver="bicgstab", lin_rtol=1e-13, lin_max_it=2000, bc_kind="constant", bc_value=0.0,
+                residual_bc=True):
+    p = L.StepParams()
+    p.flux = _flux(flux)
+    p.scheme = L.BDF2 if scheme in ("bdf2", 2) else L.BDF1
+    p.dt, p.Cvel, p.Crv = float(dt), float(Cvel), float(Crv)
+    p.newton_rtol, p.newton_atol, p.newton_max_it = newton_rtol, newton_atol, newton_max_it
+    p.solver = L.SOLVER_BY_NAME.get(solver, solver)
+    p.lin_rtol, p.lin_max_it = lin_rtol, lin_max_it
+    p.bc_kind = {"constant": L.BC_CONSTANT, "burgers_exact": L.BC_BURGERS_EXACT, "user": L.BC_USER}.get(bc_kind, bc_kind)
+    p.bc_value = float(bc_value)
+    p.residual_bc = int(bool(residual_bc))
+    return p

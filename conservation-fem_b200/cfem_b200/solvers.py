@@ -1,0 +1,152 @@
+"""Solver entry points: the reference's time loops with the per-step work on the GPU.
+
+Each function mirrors one reference script and keeps taking a dolfinx mesh (or an
+``(x, cells)`` pair) and an initial condition (callable on ``x`` with shape
+``(3|2, N)`` like ``fem.Function.interpolate``, or a nodal array):
+
+* ``solve_kpp``        ``Code/KPP/KPP_exact.py:47-166``
+* ``solve_burgers``    ``Code/Burgers_equation/Exact_Burger_RV.py:28-237``
+* ``solve_advection``  ``Code/Linear_advection/RV_node_convergence.py:48-236``
+                       (``residual_bc=True``: ``RV_node.py:213``)
+
+``dt`` / ``num_steps`` are explicit arguments because the reference derives them
+from round-off-sensitive quantities.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from .context import Context, step_params
+
+
+class _X:
+    def __init__(self, array):
+        self.array = array
+
+
+class NodalFunction:
+    """Minimal stand-in for ``dolfinx.fem.Function`` on P1: ``.x.array``, ``.name``."""
+
+    def __init__(self, array, name="f"):
+        self.x = _X(np.asarray(array, dtype=np.float64))
+        self.name = name
+
+    def __array__(self, dtype=None, copy=None):
+        return self.x.array if dtype is None else self.x.array.astype(dtype)
+
+
+def _interpolate(ctx: Context, f):
+    """``Function.interpolate``: callables get coordinates as a (3, N) array."""
+    if callable(f):
+        X = np.zeros((3, ctx.n))
+        X[0], X[1] = ctx.x[:, 0], ctx.x[:, 1]
+        v = np.asarray(f(X))
+        if v.ndim == 2:  # vector-valued (2, N) -> interleaved (N, 2)
+            return np.ascontiguousarray(v[:2].T, dtype=np.float64)
+        return np.ascontiguousarray(v, dtype=np.float64)
+    if hasattr(f, "x") and hasattr(f.x, "array"):
+        f = f.x.array
+    return np.ascontiguousarray(f, dtype=np.float64)
+
+
+# ---- problem data of the reference scripts ------------------------------------
+def kpp_initial_condition(x):
+    """``Code/KPP/KPP_exact.py:52-53``."""
+    return (x[0] ** 2 + x[1] ** 2 <= 1) * 14 * np.pi / 4 + (x[0] ** 2 + x[1] ** 2 > 1) * np.pi / 4
+
+
+def burgers_initial_condition(x):
+    """``Code/Burgers_equation/Exact_Burger_RV.py:70-80``."""
+    x0, x1 = x[0], x[1]
+    u = np.zeros_like(x0)
+    u = np.where((x0 <= 0.5) & (x1 >= 0.5), -0.2, u)
+    u = np.where((x0 > 0.5) & (x1 >= 0.5), -1.0, u)
+    u = np.where((x0 <= 0.5) & (x1 < 0.5), 0.5, u)
+    u = np.where((x0 > 0.5) & (x1 < 0.5), 0.8, u)
+    return u
+
+
+def advection_initial_condition(x, r0=0.25, x0_1=0.3, x0_2=0):
+    """``Code/Linear_advection/RV_node.py:54-55``."""
+    return 1 / 2 * (1 - np.tanh(((x[0] - x0_1) ** 2 + (x[1] - x0_2) ** 2) / r0 ** 2 - 1))
+
+
+def advection_velocity(x):
+    """``Code/Linear_advection/RV_node.py:59-60``."""
+    return np.array([-2 * np.pi * x[1], 2 * np.pi * x[0]])
+
+
+def advection_dt(w, hmax, CFL=0.5):
+    """``RV_node.py:78-85`` (matrix inf-norm of the (N,2) velocity table)."""
+    return CFL * hmax / np.linalg.norm(np.asarray(w).reshape(-1, 2), ord=np.inf)
+
+
+# ---- loops ------------------------------------------------------------------------
+def _run_scalar(flux, domain, u0, dt, num_steps, Cvel, Crv, bc_kind, bc_value, scheme, newton_rtol,
+                solver, lin_rtol, device, h, return_stats):
+    ctx = domain if isinstance(domain, Context) else Context.for_domain(domain, device=device)
+    u0 = _interpolate(ctx, u0)
+    h = ctx.nodal_h() if h is None else _interpolate(ctx, h)
+    ctx.state_set(uh=u0, u_n=u0, u_old=u0, u_oo=u0, RH=np.zeros(ctx.n), h=h, t=0.0)
+    p = step_params(flux, dt, Cvel, Crv, scheme=scheme, newton_rtol=newton_rtol, solver=solver,
+                    lin_rtol=lin_rtol, bc_kind=bc_kind, bc_value=bc_value)
+    stats = ctx.step_scalar(p, num_steps)
+    out = ctx.state_get(("uh", "eps", "RH"))
+    uh = NodalFunction(out["uh"], "uh")
+    if return_stats:
+        stats["eps"], stats["RH"], stats["h"] = out["eps"], out["RH"], h
+        return uh, stats
+    return uh
+
+
+def solve_kpp(domain, initial_condition=kpp_initial_condition, dt=0.01, num_steps=100, Cvel=0.5, Crv=4.0,
+              bc_value=np.pi / 4, scheme="bdf2", newton_rtol=1e-4, solver="bicgstab", lin_rtol=1e-13,
+              device=0, h=None, return_stats=False):
+    """KPP rotating wave, BDF2-residual RV + Crank-Nicolson Newton (``KPP_exact.py``)."""
+    return _run_scalar(L.FLUX_KPP, domain, initial_condition, dt, num_steps, Cvel, Crv, "constant", bc_value,
+                       scheme, newton_rtol, solver, lin_rtol, device, h, return_stats)
+
+
+def solve_burgers(domain, initial_condition=burgers_initial_condition, dt=None, num_steps=None, Cvel=0.5,
+                  Crv=10.0, CFL=0.5, T=0.5, scheme="bdf2", newton_rtol=1e-4, solver="bicgstab",
+                  lin_rtol=1e-13, device=0, h=None, return_stats=False):
+    """2-D inviscid Burgers Riemann problem with exact Dirichlet data (``Exact_Burger_RV.py``).
+
+    ``dt=None`` reproduces ``dt = CFL*min(h_CG)``, ``num_steps = ceil(T/dt)`` (``:105-109``).
+    """
+    ctx = domain if isinstance(domain, Context) else Context.for_domain(domain, device=device)
+    if dt is None:
+        hh = ctx.nodal_h() if h is None else _interpolate(ctx, h)
+        dt = CFL * float(np.min(hh))
+    if num_steps is None:
+        num_steps = int(np.ceil(T / dt))
+    return _run_scalar(L.FLUX_BURGERS, ctx, initial_condition, dt, num_steps, Cvel, Crv, "burgers_exact", 0.0,
+                       scheme, newton_rtol, solver, lin_rtol, device, h, return_stats)
+
+
+def solve_advection(domain, initial_condition=advection_initial_condition, velocity=advection_velocity, dt=None,
+                    num_steps=None, hmax=None, Cvel=0.25, Crv=1.0, CFL=0.5, T=1.0, residual_bc=False,
+                    solver="bicgstab", lin_rtol=1e-13, device=0, h=None, return_stats=False):
+    """Linear advection, nodal RV, CN system rebuilt each step (``RV_node_convergence.py``).
+
+    One GFEM step, then ``num_steps - 1`` RV steps, as the reference.
+    """
+    ctx = domain if isinstance(domain, Context) else Context.for_domain(domain, device=device)
+    u0 = _interpolate(ctx, initial_condition)
+    w = _interpolate(ctx, velocity)
+    if dt is None:
+        dt = advection_dt(w, hmax, CFL)
+    if num_steps is None:
+        num_steps = int(np.ceil(T / dt))
+    h = ctx.nodal_h() if h is None else _interpolate(ctx, h)
+    ctx.state_set(uh=u0, u_n=u0, u_old=u0, u_oo=u0, RH=np.zeros(ctx.n), h=h, w=w, t=0.0)
+    p = step_params(L.FLUX_ADVECTION, dt, Cvel, Crv, scheme="bdf1", solver=solver, lin_rtol=lin_rtol,
+                    bc_kind="constant", bc_value=0.0, residual_bc=residual_bc)
+    stats = ctx.step_advection(p, num_steps, first_gfem=True)
+    out = ctx.state_get(("uh", "eps", "RH"))
+    uh = NodalFunction(out["uh"], "uh")
+    if return_stats:
+        stats["eps"], stats["RH"], stats["h"], stats["dt"] = out["eps"], out["RH"], h, dt
+        return uh, stats
+    return uh

@@ -1,0 +1,704 @@
+// extern "C" surface (include/cfem_b200.h): context life cycle, host/device
+// argument staging with the internal<->caller permutation, the single-operator
+// entry points, and the time loops.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "device_utils.cuh"
+#include "launch.h"
+
+using namespace cfem;
+
+namespace cfem {
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+}  // namespace cfem
+
+#define API_BEGIN try {
+#define API_END                                                   \
+  return 0;                                                       \
+  }                                                               \
+  catch (const cfem::Error& e) { cfem::set_error(e.msg); return e.code; } \
+  catch (const std::exception& e) { cfem::set_error(e.what()); return -9; }
+
+namespace {
+
+template <class T>
+T* dalloc(cfem_ctx* c, int64_t count) {
+  void* p = nullptr;
+  const size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T);
+  CUDA_OK(cudaMalloc(&p, bytes));
+  c->allocs.push_back(p);
+  c->bytes += (int64_t)bytes;
+  return (T*)p;
+}
+template <class T>
+T* upload(cfem_ctx* c, const std::vector<T>& v) {
+  T* d = dalloc<T>(c, (int64_t)v.size());
+  if (!v.empty()) CUDA_OK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// caller array (host or device, caller numbering) -> internal-order device vector
+void import_vec(cfem_ctx* c, const double* user, double* dst, int stage_slot = 0) {
+  const int64_t n = c->dm.nn;
+  const double* src = user;
+  if (!is_device_ptr(user)) {
+    CUDA_OK(cudaMemcpyAsync(c->stage[stage_slot], user, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    src = c->stage[stage_slot];
+  }
+  launch_gather(c, src, c->d_n2u, dst, n);
+}
+void import_vec2(cfem_ctx* c, const double* user, double2* dst) {
+  const int64_t n = c->dm.nn;
+  const double2* src = (const double2*)user;
+  if (!is_device_ptr(user)) {
+    // stage[2] and stage[3] are contiguous (allocated as one block)
+    CUDA_OK(cudaMemcpyAsync(c->stage[2], user, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    src = (const double2*)c->stage[2];
+  }
+  launch_gather2(c, src, c->d_n2u, dst, n);
+}
+// internal-order device vector -> caller array (synchronous for host destinations)
+void export_vec(cfem_ctx* c, const double* internal, double* user) {
+  const int64_t n = c->dm.nn;
+  if (is_device_ptr(user)) {
+    launch_gather(c, internal, c->d_u2n, user, n);
+  } else {
+    launch_gather(c, internal, c->d_u2n, c->stage[1], n);
+    CUDA_OK(cudaMemcpyAsync(user, c->stage[1], n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+}
+
+// Dirichlet values in caller's bc order -> nodal g (internal), zero if null
+void import_bc(cfem_ctx* c, const double* bc_values) {
+  if (!bc_values) { launch_bc_values(c, CFEM_BC_CONSTANT, 0.0, 0.0, nullptr, c->g); return; }
+  const double* src = bc_values;
+  if (!is_device_ptr(bc_values)) {
+    CUDA_OK(cudaMemcpyAsync(c->stage[0], bc_values, c->nbc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    src = c->stage[0];
+  }
+  launch_bc_values(c, CFEM_BC_USER, 0.0, 0.0, src, c->g);
+}
+
+void apply_dirichlet(cfem_ctx* c, const int32_t* dofs, int64_t n) {
+  const int64_t nn = c->dm.nn;
+  std::vector<uint8_t> flag(nn, 0);
+  std::vector<int32_t> nodes(n);
+  c->bc_user.assign(dofs, dofs + n);
+  for (int64_t j = 0; j < n; ++j) {
+    if (dofs[j] < 0 || dofs[j] >= nn) CFEM_THROW(-1, "Dirichlet dof out of range");
+    nodes[j] = c->hm.u2n[dofs[j]];
+    flag[nodes[j]] = 1;
+  }
+  CUDA_OK(cudaMemcpy(c->d_is_bc, flag.data(), nn, cudaMemcpyHostToDevice));
+  if (n > 0) CUDA_OK(cudaMemcpy(c->d_bc_nodes, nodes.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  c->nbc = n;
+  launch_mass(c, c->mat[CFEM_MAT_MASS_BC], true);
+  launch_fill(c, c->g, 0.0, nn);
+}
+
+Matrix& get_matrix(cfem_ctx* c, int which) {
+  if (which < 0 || which > 3) CFEM_THROW(-1, "unknown matrix id");
+  if (!c->mat[which].valid) CFEM_THROW(-1, "matrix has not been assembled yet");
+  return c->mat[which];
+}
+
+void build_user_csr(cfem_ctx* c) {
+  if (!c->u_rowptr.empty()) return;
+  const HostMesh& hm = c->hm;
+  const int64_t nn = hm.nn;
+  c->u_rowptr.assign(nn + 1, 0);
+  for (int64_t u = 0; u < nn; ++u) {
+    const int32_t i = hm.u2n[u];
+    c->u_rowptr[u + 1] = c->u_rowptr[u] + (hm.rowptr[i + 1] - hm.rowptr[i]);
+  }
+  c->u_colidx.resize(hm.nnz);
+  c->u_slot.resize(hm.nnz);
+#pragma omp parallel for schedule(static)
+  for (int64_t u = 0; u < nn; ++u) {
+    const int32_t i = hm.u2n[u];
+    const int len = hm.rowptr[i + 1] - hm.rowptr[i];
+    std::pair<int32_t, int32_t> tmp[kMaxRow];
+    for (int k = 0; k < len; ++k) tmp[k] = {hm.n2u[hm.colidx[hm.rowptr[i] + k]], hm.rowptr[i] + k};
+    std::sort(tmp, tmp + len);
+    for (int k = 0; k < len; ++k) {
+      c->u_colidx[c->u_rowptr[u] + k] = tmp[k].first;
+      c->u_slot[c->u_rowptr[u] + k] = tmp[k].second;
+    }
+  }
+}
+
+SolveResult run_solver(cfem_ctx* c, int solver, const Matrix& A, const double* b, double* x, double rtol,
+                       double atol, int max_it, int* predict) {
+  switch (solver) {
+    case CFEM_SOLVER_PCG: return pcg(c, A, b, x, rtol, atol, max_it, predict);
+    case CFEM_SOLVER_BICGSTAB: return bicgstab(c, A, b, x, rtol, atol, max_it, predict);
+    case CFEM_SOLVER_GMRES: return gmres(c, A, b, x, rtol, atol, max_it, predict);
+    default: CFEM_THROW(-1, "unknown solver id");
+  }
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+const char* cfem_last_error(void) { return g_error.c_str(); }
+int cfem_version(void) { return 100; }
+int cfem_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int cfem_create(cfem_ctx** out, int device, int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
+                const void* cells, int cell_index_bytes, int order) {
+  cfem_ctx* c = nullptr;
+  API_BEGIN
+  if (!out || !x || !cells) CFEM_THROW(-1, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    CFEM_THROW(-2, "no CUDA device: cfem_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) CFEM_THROW(-1, "device index out of range");
+  c = new cfem_ctx();
+  c->device = device;
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  analyse_mesh(c->hm, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order);
+  HostMesh& hm = c->hm;
+  const int64_t nn = hm.nn;
+  DevMesh& dm = c->dm;
+  dm.nn = nn; dm.nc = hm.nc; dm.nnz = hm.nnz;
+  dm.ntiles = (int)hm.tile_node.size() - 1;
+  dm.xy = (const double2*)upload(c, hm.xy);
+  dm.cells = upload(c, hm.cells);
+  dm.rowptr = upload(c, hm.rowptr);
+  dm.colidx = upload(c, hm.colidx);
+  dm.v2c_ptr = upload(c, hm.v2c_ptr);
+  dm.v2c_code = upload(c, hm.v2c_code);
+  dm.tile_node = upload(c, hm.tile_node);
+  dm.tile_cellptr = upload(c, hm.tile_cellptr);
+  dm.tile_cells = upload(c, hm.tile_cells);
+  c->d_n2u = upload(c, hm.n2u);
+  c->d_u2n = upload(c, hm.u2n);
+  c->d_is_bnd = upload(c, hm.is_bnd);
+  c->d_is_bc = dalloc<uint8_t>(c, nn);
+  dm.is_bc = c->d_is_bc;
+  c->d_bc_nodes = dalloc<int32_t>(c, nn);
+  // host-side copies that are only needed on the device from here on
+  std::vector<double>().swap(hm.xy);
+  std::vector<int32_t>().swap(hm.cells);
+  std::vector<uint32_t>().swap(hm.v2c_code);
+  std::vector<int32_t>().swap(hm.v2c_ptr);
+  std::vector<int32_t>().swap(hm.tile_cells);
+  for (int k = 0; k < 4; ++k) {
+    c->mat[k].vals = dalloc<double>(c, hm.nnz);
+    c->mat[k].dinv = dalloc<double>(c, nn);
+  }
+  double** state[] = {&c->uh, &c->u_n, &c->u_old, &c->u_oo, &c->RH, &c->eps, &c->h, &c->g, &c->fluxn};
+  for (double** s : state) { *s = dalloc<double>(c, nn); CUDA_OK(cudaMemsetAsync(*s, 0, nn * sizeof(double), c->stream)); }
+  c->w = (double2*)dalloc<double>(c, 2 * nn);
+  CUDA_OK(cudaMemsetAsync(c->w, 0, 2 * nn * sizeof(double), c->stream));
+  for (int k = 0; k < 10; ++k) c->wk[k] = dalloc<double>(c, nn);
+  c->stage[0] = dalloc<double>(c, nn);
+  c->stage[1] = dalloc<double>(c, nn);
+  c->stage[2] = dalloc<double>(c, 2 * nn);
+  c->stage[3] = c->stage[2] + nn;
+  c->partials = dalloc<double>(c, 8 * (int64_t)kMaxPartials);
+  c->scalars = dalloc<double>(c, 32);
+  c->status = dalloc<int32_t>(c, 8);
+  CUDA_OK(cudaMemsetAsync(c->status, 0, 8 * sizeof(int32_t), c->stream));
+  CUDA_OK(cudaMemsetAsync(c->scalars, 0, 32 * sizeof(double), c->stream));
+  CUDA_OK(cudaMallocHost((void**)&c->h_pinned, (64 + kMaxPartials) * sizeof(double)));
+  CUDA_OK(cudaMallocHost((void**)&c->h_status, 8 * sizeof(int32_t)));
+  if (hm.max_tile_cells > kTileCellCap || hm.max_tile_nnz > kTileNnzCap) CFEM_THROW(-1, "tile capacity exceeded");
+  launch_mass(c, c->mat[CFEM_MAT_MASS], false);
+  // every boundary dof is a Dirichlet dof by default (reference loops: KPP_exact.py:85-89)
+  apply_dirichlet(c, hm.bnd_user_sorted.data(), (int64_t)hm.bnd_user_sorted.size());
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+  }
+  catch (const cfem::Error& e) { cfem::set_error(e.msg); if (c) cfem_destroy(c); return e.code; }
+  catch (const std::exception& e) { cfem::set_error(e.what()); if (c) cfem_destroy(c); return -9; }
+}
+
+void cfem_destroy(cfem_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int cfem_synchronize(cfem_ctx* c) {
+  API_BEGIN
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int64_t cfem_num_nodes(const cfem_ctx* c) { return c->dm.nn; }
+int64_t cfem_num_cells(const cfem_ctx* c) { return c->dm.nc; }
+int64_t cfem_num_nonzeros(const cfem_ctx* c) { return c->dm.nnz; }
+int64_t cfem_num_boundary(const cfem_ctx* c) { return (int64_t)c->hm.bnd_user_sorted.size(); }
+int64_t cfem_num_dirichlet(const cfem_ctx* c) { return c->nbc; }
+int64_t cfem_num_tiles(const cfem_ctx* c) { return c->dm.ntiles; }
+int64_t cfem_device_bytes(const cfem_ctx* c) { return c->bytes; }
+
+int cfem_get_csr_pattern(cfem_ctx* c, int32_t* rowptr, int32_t* colidx) {
+  API_BEGIN
+  build_user_csr(c);
+  if (rowptr) std::memcpy(rowptr, c->u_rowptr.data(), c->u_rowptr.size() * sizeof(int32_t));
+  if (colidx) std::memcpy(colidx, c->u_colidx.data(), c->u_colidx.size() * sizeof(int32_t));
+  API_END
+}
+
+int cfem_get_boundary_dofs(cfem_ctx* c, int32_t* dofs) {
+  API_BEGIN
+  std::memcpy(dofs, c->hm.bnd_user_sorted.data(), c->hm.bnd_user_sorted.size() * sizeof(int32_t));
+  API_END
+}
+
+int cfem_set_dirichlet(cfem_ctx* c, const int32_t* dofs, int64_t n) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (n < 0 || (n > 0 && !dofs)) CFEM_THROW(-1, "bad Dirichlet set");
+  apply_dirichlet(c, dofs, n);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_get_ordering(cfem_ctx* c, int32_t* n2u) {
+  API_BEGIN
+  std::memcpy(n2u, c->hm.n2u.data(), c->hm.n2u.size() * sizeof(int32_t));
+  API_END
+}
+
+int cfem_nodal_h(cfem_ctx* c, double* h_out, double rtol, int max_it, int* iters) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  double* b = c->wk[8];
+  launch_nodal_h_rhs(c, b);
+  launch_fill(c, c->h, 0.0, c->dm.nn);
+  int predict = 24;
+  SolveResult r = pcg(c, c->mat[CFEM_MAT_MASS], b, c->h, rtol, 0.0, max_it, &predict);
+  if (iters) *iters = r.iters;
+  if (h_out) export_vec(c, c->h, h_out);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (!r.converged) CFEM_THROW(-3, "nodal_h: PCG did not converge");
+  API_END
+}
+
+int cfem_rv_residual(cfem_ctx* c, int flux, int scheme, double dt, const double* u_n, const double* u_old,
+                     const double* u_oo, const double* w, int use_bc, double* R_io, double rtol, int max_it,
+                     int* iters) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!u_n || !u_old || !R_io) CFEM_THROW(-1, "rv_residual: null argument");
+  if (scheme != CFEM_BDF1 && scheme != CFEM_BDF2) CFEM_THROW(-1, "rv_residual: unknown scheme");
+  import_vec(c, u_n, c->u_n);
+  import_vec(c, u_old, c->u_old);
+  if (u_oo) import_vec(c, u_oo, c->u_oo);
+  if (w) import_vec2(c, w, c->w);
+  import_vec(c, R_io, c->RH);
+  double* b = c->wk[8];
+  launch_rv_rhs(c, flux, scheme, dt, c->u_n, c->u_old, u_oo ? c->u_oo : nullptr, w ? c->w : nullptr, use_bc != 0, b,
+                nullptr);
+  SolveResult r = pcg(c, c->mat[use_bc ? CFEM_MAT_MASS_BC : CFEM_MAT_MASS], b, c->RH, rtol, 0.0, max_it, &c->pcg_predict);
+  if (iters) *iters = r.iters;
+  export_vec(c, c->RH, R_io);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (!r.converged) CFEM_THROW(-3, "rv_residual: PCG did not converge");
+  API_END
+}
+
+int cfem_rv_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv, const double* uh,
+                    const double* u_n, double* Rh, const double* h, const double* w, double* eps_out) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!eps_out) CFEM_THROW(-1, "rv_epsilon: null output");
+  if (uh) import_vec(c, uh, c->uh);
+  if (u_n) import_vec(c, u_n, c->u_n);
+  if (Rh) import_vec(c, Rh, c->RH);
+  if (h) import_vec(c, h, c->h);
+  if (w) import_vec2(c, w, c->w);
+  launch_epsilon(c, variant, flux, Cvel, Crv, uh ? c->uh : nullptr, u_n ? c->u_n : nullptr, Rh ? c->RH : nullptr,
+                 h ? c->h : nullptr, w ? c->w : nullptr, c->eps);
+  export_vec(c, c->eps, eps_out);
+  if (variant == CFEM_EPS_LINEAR_SIMPLE && Rh) export_vec(c, c->RH, Rh);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_assemble_advection(cfem_ctx* c, double dt, const double* w, const double* eps, const double* u_n,
+                            const double* bc_values, double* b_out) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!w || !u_n) CFEM_THROW(-1, "assemble_advection: null argument");
+  import_vec2(c, w, c->w);
+  if (eps) import_vec(c, eps, c->eps);
+  import_vec(c, u_n, c->u_n);
+  import_bc(c, bc_values);
+  launch_adv_system(c, dt, c->w, eps ? c->eps : nullptr, c->u_n, c->g, c->mat[CFEM_MAT_SYSTEM], c->wk[8]);
+  if (b_out) export_vec(c, c->wk[8], b_out);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_assemble_cn_residual(cfem_ctx* c, int flux, double dt, const double* uh, const double* u_n,
+                              const double* eps, const double* bc_values, double* F_out) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!uh || !u_n || !eps || !F_out) CFEM_THROW(-1, "assemble_cn_residual: null argument");
+  import_vec(c, uh, c->uh);
+  import_vec(c, u_n, c->u_n);
+  import_vec(c, eps, c->eps);
+  import_bc(c, bc_values);
+  launch_cn_residual(c, flux, dt, c->uh, c->u_n, c->eps, c->g, nullptr, c->wk[8], nullptr);
+  export_vec(c, c->wk[8], F_out);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_assemble_cn_jacobian(cfem_ctx* c, int flux, double dt, const double* uh, const double* eps) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!uh || !eps) CFEM_THROW(-1, "assemble_cn_jacobian: null argument");
+  import_vec(c, uh, c->uh);
+  import_vec(c, eps, c->eps);
+  launch_cn_jacobian(c, flux, dt, c->uh, c->eps, c->mat[CFEM_MAT_SYSTEM]);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_assemble_stiffness(cfem_ctx* c, const double* eps) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (eps) import_vec(c, eps, c->eps);
+  launch_stiffness(c, c->mat[CFEM_MAT_STIFFNESS], eps ? c->eps : nullptr);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_matrix_values(cfem_ctx* c, int which, double* vals_out) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  Matrix& A = get_matrix(c, which);
+  build_user_csr(c);
+  std::vector<double> tmp(c->hm.nnz);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaMemcpy(tmp.data(), A.vals, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (is_device_ptr(vals_out)) CFEM_THROW(-1, "matrix_values: output must be host memory");
+  for (int64_t s = 0; s < c->hm.nnz; ++s) vals_out[s] = tmp[c->u_slot[s]];
+  API_END
+}
+
+int cfem_spmv(cfem_ctx* c, int which, const double* x, double* y) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  Matrix& A = get_matrix(c, which);
+  import_vec(c, x, c->wk[8]);
+  launch_spmv(c, A, c->wk[8], c->wk[9]);
+  export_vec(c, c->wk[9], y);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_solve(cfem_ctx* c, int which, int solver, const double* b, double* x_io, double rtol, double atol,
+               int max_it, int* iters, double* relres) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  Matrix& A = get_matrix(c, which);
+  import_vec(c, b, c->wk[8]);
+  import_vec(c, x_io, c->wk[9]);
+  int predict = 8;
+  SolveResult r = run_solver(c, solver, A, c->wk[8], c->wk[9], rtol, atol, max_it, &predict);
+  if (iters) *iters = r.iters;
+  if (relres) *relres = r.relres;
+  export_vec(c, c->wk[9], x_io);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (!r.converged) CFEM_THROW(-3, "solve: Krylov solver did not converge");
+  API_END
+}
+
+int cfem_state_set(cfem_ctx* c, const double* uh, const double* u_n, const double* u_old, const double* u_oo,
+                   const double* RH, const double* h, const double* w, double t) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (uh) import_vec(c, uh, c->uh);
+  if (u_n) import_vec(c, u_n, c->u_n);
+  if (u_old) import_vec(c, u_old, c->u_old);
+  if (u_oo) import_vec(c, u_oo, c->u_oo);
+  if (RH) import_vec(c, RH, c->RH);
+  if (h) import_vec(c, h, c->h);
+  if (w) import_vec2(c, w, c->w);
+  c->t = t;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_state_get(cfem_ctx* c, double* uh, double* u_n, double* u_old, double* u_oo, double* RH, double* eps,
+                   double* t) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (uh) export_vec(c, c->uh, uh);
+  if (u_n) export_vec(c, c->u_n, u_n);
+  if (u_old) export_vec(c, c->u_old, u_old);
+  if (u_oo) export_vec(c, c->u_oo, u_oo);
+  if (RH) export_vec(c, c->RH, RH);
+  if (eps) export_vec(c, c->eps, eps);
+  if (t) *t = c->t;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+// sqrt(sum of the per-CTA partials) on the host (one sync)
+static double partials_norm(cfem_ctx* c, const double* part, int npart) {
+  double* tmp = c->h_pinned + 64;
+  CUDA_OK(cudaMemcpyAsync(tmp, part, npart * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  double s = 0.0;
+  for (int i = 0; i < npart; ++i) s += tmp[i];
+  return sqrt(s);
+}
+
+int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const double* bc_values,
+                     cfem_step_stats* stats) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!p) CFEM_THROW(-1, "step_scalar: null params");
+  if (p->flux != CFEM_FLUX_BURGERS && p->flux != CFEM_FLUX_KPP) CFEM_THROW(-1, "step_scalar: flux must be BURGERS or KPP");
+  if (!(p->dt > 0.0)) CFEM_THROW(-1, "step_scalar: dt must be positive");
+  const int64_t nn = c->dm.nn;
+  const Launches l0 = c->launches;
+  cfem_step_stats st{};
+  const double* d_bc_user = nullptr;
+  if (p->bc_kind == CFEM_BC_USER) {
+    if (!bc_values) CFEM_THROW(-1, "step_scalar: CFEM_BC_USER needs bc_values");
+    if (is_device_ptr(bc_values)) d_bc_user = bc_values;
+    else {
+      if ((int64_t)n_steps * c->nbc > 2 * nn) CFEM_THROW(-1, "step_scalar: too many user bc values for one call");
+      CUDA_OK(cudaMemcpyAsync(c->stage[2], bc_values, (size_t)n_steps * c->nbc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      d_bc_user = c->stage[2];
+    }
+  }
+  double* b = c->wk[8];
+  double* F = c->wk[8];
+  double* dx = c->wk[9];
+  double* normpart = c->partials + 7 * kMaxPartials;
+  Matrix& J = c->mat[CFEM_MAT_SYSTEM];
+  for (int s = 0; s < n_steps; ++s) {
+    c->t += p->dt;
+    launch_bc_values(c, p->bc_kind, p->bc_value, c->t, d_bc_user ? d_bc_user + (int64_t)s * c->nbc : nullptr, c->g);
+    // (a-3) residual projection  M_bc RH = b
+    launch_rv_rhs(c, p->flux, p->scheme, p->dt, c->u_n, c->u_old, c->u_oo, nullptr, true, b, c->fluxn);
+    SolveResult rm = pcg(c, c->mat[CFEM_MAT_MASS_BC], b, c->RH, p->lin_rtol, 0.0, p->lin_max_it, &c->pcg_predict);
+    if (!rm.converged) CFEM_THROW(-3, "step_scalar: residual PCG did not converge");
+    st.mass_iterations += rm.iters;
+    // (a-4) nodal viscosity
+    launch_epsilon(c, CFEM_EPS_NONLINEAR, p->flux, p->Cvel, p->Crv, c->uh, c->u_n, c->RH, c->h, nullptr, c->eps);
+    // (a-8) Newton on the Crank-Nicolson residual, dolfinx NewtonSolver 'residual' criterion
+    int np = launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, c->fluxn, F, normpart);
+    double res = partials_norm(c, normpart, np);
+    const double res0 = res;
+    bool converged = res < p->newton_atol;
+    int it = 0;
+    while (!converged && it < p->newton_max_it) {
+      launch_cn_jacobian(c, p->flux, p->dt, c->uh, c->eps, J);
+      launch_fill(c, dx, 0.0, nn);
+      SolveResult rk = run_solver(c, p->solver, J, F, dx, p->lin_rtol, 0.0, p->lin_max_it, &c->krylov_predict);
+      if (!rk.converged) CFEM_THROW(-3, "step_scalar: Krylov solve did not converge (relres " + std::to_string(rk.relres) + ")");
+      st.krylov_iterations += rk.iters;
+      launch_sub(c, c->uh, dx, nn);
+      ++it;
+      np = launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, c->fluxn, F, normpart);
+      res = partials_norm(c, normpart, np);
+      converged = (res / res0 < p->newton_rtol) || (res < p->newton_atol);
+    }
+    st.newton_iterations += it;
+    st.last_newton_residual = res;
+    if (!converged) CFEM_THROW(-3, "Newton solver did not converge in " + std::to_string(it) + " iterations");
+    // rotate  u_oo <- u_old <- u_n <- uh   (KPP_exact.py:159-161)
+    double* tmp = c->u_oo;
+    c->u_oo = c->u_old;
+    c->u_old = c->u_n;
+    c->u_n = tmp;
+    launch_copy(c, c->u_n, c->uh, nn);
+    st.steps++;
+  }
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  st.time = c->t;
+  st.kernel_launches = c->launches.total - l0.total;
+  st.spmv_launches = c->launches.spmv - l0.spmv;
+  st.assembly_launches = c->launches.assembly - l0.assembly;
+  if (stats) *stats = st;
+  API_END
+}
+
+int cfem_step_advection(cfem_ctx* c, const cfem_step_params* p, int n_steps, int first_gfem,
+                        cfem_step_stats* stats) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!p) CFEM_THROW(-1, "step_advection: null params");
+  if (!(p->dt > 0.0)) CFEM_THROW(-1, "step_advection: dt must be positive");
+  const int64_t nn = c->dm.nn;
+  const Launches l0 = c->launches;
+  cfem_step_stats st{};
+  double* b = c->wk[8];
+  Matrix& A = c->mat[CFEM_MAT_SYSTEM];
+  launch_bc_values(c, CFEM_BC_CONSTANT, p->bc_kind == CFEM_BC_CONSTANT ? p->bc_value : 0.0, 0.0, nullptr, c->g);
+  for (int s = 0; s < n_steps; ++s) {
+    c->t += p->dt;
+    const bool gfem = first_gfem && s == 0;
+    if (!gfem) {
+      // (a-3) BDF1 residual projection, RV_node.py:209-214
+      launch_rv_rhs(c, CFEM_FLUX_ADVECTION, CFEM_BDF1, p->dt, c->u_n, c->u_old, nullptr, c->w, p->residual_bc != 0, b, nullptr);
+      SolveResult rm = pcg(c, c->mat[p->residual_bc ? CFEM_MAT_MASS_BC : CFEM_MAT_MASS], b, c->RH, p->lin_rtol, 0.0,
+                           p->lin_max_it, &c->pcg_predict);
+      if (!rm.converged) CFEM_THROW(-3, "step_advection: residual PCG did not converge");
+      st.mass_iterations += rm.iters;
+      // (a-5) nodal viscosity
+      launch_epsilon(c, CFEM_EPS_LINEAR, CFEM_FLUX_ADVECTION, p->Cvel, p->Crv, c->uh, c->u_n, c->RH, c->h, c->w, c->eps);
+    }
+    // (a-7) CN system + rhs, RV_node.py:220-242
+    launch_adv_system(c, p->dt, c->w, gfem ? nullptr : c->eps, c->u_n, c->g, A, b);
+    SolveResult rk = run_solver(c, p->solver, A, b, c->uh, p->lin_rtol, 0.0, p->lin_max_it, &c->krylov_predict);
+    if (!rk.converged) CFEM_THROW(-3, "step_advection: Krylov solve did not converge");
+    st.krylov_iterations += rk.iters;
+    if (gfem) {
+      launch_copy(c, c->u_n, c->uh, nn);  // u_old keeps the initial condition (RV_node.py:157)
+    } else {
+      double* tmp = c->u_old;
+      c->u_old = c->u_n;
+      c->u_n = tmp;
+      launch_copy(c, c->u_n, c->uh, nn);
+    }
+    st.steps++;
+  }
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  st.time = c->t;
+  st.kernel_launches = c->launches.total - l0.total;
+  st.spmv_launches = c->launches.spmv - l0.spmv;
+  st.assembly_launches = c->launches.assembly - l0.assembly;
+  if (stats) *stats = st;
+  API_END
+}
+
+int cfem_time_kernel(cfem_ctx* c, int kernel, int flux, int reps, double* ms_per_launch, double* algorithmic_bytes) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (reps < 1) reps = 1;
+  const double nn = (double)c->dm.nn, nc = (double)c->dm.nc, nnz = (double)c->dm.nnz;
+  const double dt = 1e-3;
+  // adjacency + tiling metadata every assembly launch streams: tile cell lists (4 B per
+  // tile-cell), connectivity (12 B per tile-cell), codes (4 B per (node,cell) = 3 Nc),
+  // v2c_ptr + rowptr + tile tables; coordinates 16 B per node.
+  const double tile_cells = (double)c->dm.nc * 1.0;  // lower bound: every cell staged once
+  const double meta = 16.0 * tile_cells + 4.0 * 3.0 * nc + 8.0 * nn + 16.0 * nn;
+  double bytes = 0.0;
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  Matrix& M = c->mat[CFEM_MAT_MASS_BC];
+  Matrix& J = c->mat[CFEM_MAT_SYSTEM];
+  auto body = [&]() {
+    switch (kernel) {
+      case CFEM_KERNEL_SPMV: launch_spmv(c, M, c->u_n, c->wk[9]); bytes = 12.0 * nnz + 4.0 * (nn + 1) + 16.0 * nn; break;
+      case CFEM_KERNEL_ASM_RESIDUAL:
+        launch_cn_residual(c, flux, dt, c->uh, c->u_n, c->eps, c->g, c->fluxn, c->wk[8], c->partials + 7 * kMaxPartials);
+        bytes = meta + 8.0 * 5 * nn + 8.0 * nn; break;   // uh,u_n,eps,g,fluxn in; F out
+      case CFEM_KERNEL_ASM_JACOBIAN:
+        launch_cn_jacobian(c, flux, dt, c->uh, c->eps, J);
+        bytes = meta + 8.0 * 2 * nn + 8.0 * nnz + 8.0 * nn; break;  // uh,eps in; vals + dinv out
+      case CFEM_KERNEL_RV_EPSILON:
+        launch_epsilon(c, CFEM_EPS_NONLINEAR, flux, 0.5, 4.0, c->uh, c->u_n, c->RH, c->h, nullptr, c->eps);
+        bytes = 8.0 * 4 * nn + 16.0 * nn + 4.0 * nnz + 4.0 * nn + 8.0 * nn; break;  // uh,u_n,Rh,h; beta w+r; graph; eps
+      case CFEM_KERNEL_ASM_RV_RHS:
+        launch_rv_rhs(c, flux, CFEM_BDF2, dt, c->u_n, c->u_old, c->u_oo, nullptr, true, c->wk[8], c->fluxn);
+        bytes = meta + 8.0 * 3 * nn + 16.0 * nn; break;
+      default: CFEM_THROW(-1, "time_kernel: unknown kernel id");
+    }
+  };
+  body();  // warm-up (also sets function attributes)
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaEventRecord(e0, c->stream));
+  for (int r = 0; r < reps; ++r) body();
+  CUDA_OK(cudaEventRecord(e1, c->stream));
+  CUDA_OK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_per_launch) *ms_per_launch = (double)ms / reps;
+  if (algorithmic_bytes) *algorithmic_bytes = bytes;
+  API_END
+}
+
+}  // extern "C"
+
+// ---- host analysis without a device ------------------------------------------
+struct cfem_host_mesh { cfem::HostMesh hm; };
+
+template <class F>
+static auto host_array(const cfem_host_mesh* h, int what, F&& f) {
+  const HostMesh& m = h->hm;
+  switch (what) {
+    case CFEM_HM_N2U: return f(m.n2u.data(), m.n2u.size(), 4);
+    case CFEM_HM_CELLS: return f(m.cells.data(), m.cells.size(), 4);
+    case CFEM_HM_ROWPTR: return f(m.rowptr.data(), m.rowptr.size(), 4);
+    case CFEM_HM_COLIDX: return f(m.colidx.data(), m.colidx.size(), 4);
+    case CFEM_HM_V2C_PTR: return f(m.v2c_ptr.data(), m.v2c_ptr.size(), 4);
+    case CFEM_HM_V2C_CODE: return f(m.v2c_code.data(), m.v2c_code.size(), 4);
+    case CFEM_HM_TILE_NODE: return f(m.tile_node.data(), m.tile_node.size(), 4);
+    case CFEM_HM_TILE_CELLPTR: return f(m.tile_cellptr.data(), m.tile_cellptr.size(), 4);
+    case CFEM_HM_TILE_CELLS: return f(m.tile_cells.data(), m.tile_cells.size(), 4);
+    case CFEM_HM_IS_BND: return f(m.is_bnd.data(), m.is_bnd.size(), 1);
+    case CFEM_HM_BND_USER: return f(m.bnd_user_sorted.data(), m.bnd_user_sorted.size(), 4);
+    default: return f(nullptr, (size_t)0, 0);
+  }
+}
+
+extern "C" {
+
+int cfem_host_analyse(cfem_host_mesh** out, int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
+                      const void* cells, int cell_index_bytes, int order) {
+  cfem_host_mesh* h = nullptr;
+  try {
+    if (!out || !x || !cells) CFEM_THROW(-1, "null argument");
+    h = new cfem_host_mesh();
+    analyse_mesh(h->hm, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order);
+    *out = h;
+    return 0;
+  } catch (const cfem::Error& e) { cfem::set_error(e.msg); delete h; return e.code; }
+  catch (const std::exception& e) { cfem::set_error(e.what()); delete h; return -9; }
+}
+
+int64_t cfem_host_size(const cfem_host_mesh* h, int what) {
+  return host_array(h, what, [](const void*, size_t n, int) { return (int64_t)n; });
+}
+int cfem_host_copy(const cfem_host_mesh* h, int what, void* dst) {
+  int64_t n = host_array(h, what, [&](const void* p, size_t n, int es) { if (p && n) std::memcpy(dst, p, n * es); return (int64_t)n; });
+  return n >= 0 ? 0 : -1;
+}
+void cfem_host_free(cfem_host_mesh* h) { delete h; }
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Device helpers: deterministic block reductions, geometry, quadrature tables.
+#pragma once
+#include "internal.h"
+
+namespace cfem {
+
+constexpr int kBlock = 256;  // threads per CTA for every kernel in the library
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum over the CTA (blockDim.x == kBlock), result valid in every thread.
+// Fixed shuffle tree + fixed warp order -> bitwise reproducible.
+__device__ __forceinline__ double block_sum(double v, double* sh /* >= 9 doubles */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = lane < (kBlock / 32) ? sh[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) sh[8] = t;
+  }
+  __syncthreads();
+  return sh[8];
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = lane < (kBlock / 32) ? sh[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) sh[8] = t;
+  }
+  __syncthreads();
+  return sh[8];
+}
+__device__ __forceinline__ double block_min(double v, double* sh) { return -block_max(-v, sh); }
+
+// Every CTA re-reduces the per-CTA partials a previous kernel wrote (n small,
+// L2-resident): removes separate "finalise" launches, keeps a fixed order.
+__device__ __forceinline__ double reduce_partials(const double* __restrict__ p, int n, double* sh) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += kBlock) s += p[i];
+  return block_sum(s, sh);
+}
+
+struct CellGeom {
+  double gx[3], gy[3];  // gradients of the three P1 basis functions
+  double area;
+};
+
+__device__ __forceinline__ CellGeom cell_geom(const double2 p0, const double2 p1, const double2 p2) {
+  CellGeom g;
+  const double e1x = p1.x - p0.x, e1y = p1.y - p0.y;
+  const double e2x = p2.x - p0.x, e2y = p2.y - p0.y;
+  const double det = e1x * e2y - e1y * e2x;
+  const double inv = 1.0 / det;
+  g.gx[1] = e2y * inv;
+  g.gy[1] = -e2x * inv;
+  g.gx[2] = -e1y * inv;
+  g.gy[2] = e1x * inv;
+  g.gx[0] = -g.gx[1] - g.gx[2];
+  g.gy[0] = -g.gy[1] - g.gy[2];
+  g.area = 0.5 * fabs(det);
+  return g;
+}
+
+// Symmetric triangle rules (barycentric points, weights sum to 1):
+// degree 4 / 6 points and degree 5 / 7 points — the rules FFCx selects for the
+// KPP residual and Jacobian forms.
+constexpr double kQ4a = 0.4459484909159648863183292538830519883991;
+constexpr double kQ4b = 0.09157621350977074345957146340220150785433;
+constexpr double kQ4wa = 0.2233815896780114656950070084331228043703;
+constexpr double kQ4wb = 0.1099517436553218676383263249002105289631;
+constexpr double kQ5a = 0.1012865073234563388009873619151238280556;
+constexpr double kQ5b = 0.4701420641051150897704412095134476005159;
+constexpr double kQ5wa = 0.1259391805448271525956839455001813336576;
+constexpr double kQ5wb = 0.1323941527885061807376493878331519996757;
+constexpr double kQ5w0 = 0.225;
+
+}  // namespace cfem

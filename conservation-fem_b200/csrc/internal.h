@@ -1,0 +1,119 @@
+// Internal declarations shared by the cfem_b200 translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cfem_b200.h"
+
+namespace cfem {
+
+// ---- error plumbing -----------------------------------------------------
+void set_error(const std::string& msg);
+struct Error { std::string msg; int code; };
+#define CFEM_THROW(code, msg) throw ::cfem::Error{std::string(msg), (code)}
+#define CUDA_OK(call)                                                                  \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      CFEM_THROW(-2, std::string(#call) + ": " + cudaGetErrorString(_e) + " at " +     \
+                         __FILE__ + ":" + std::to_string(__LINE__));                   \
+  } while (0)
+
+// ---- tile / adjacency encoding --------------------------------------------
+// One 32-bit code per (node, incident cell):
+//   bits  0..12  index of the cell in the tile's cell list (<= 8191)
+//   bits 13..14  local vertex number k of the node inside that cell
+//   bits 15..19 / 20..24 / 25..29  position, inside the node's CSR row, of the
+//                columns of the cell's vertices 0 / 1 / 2
+constexpr int kCodeCellBits = 13;
+constexpr int kMaxRow = 32;          // 5-bit positions
+constexpr int kTileNodes = 256;      // nodes per assembly tile (== threads per CTA)
+constexpr int kTileCellCap = 768;    // cells staged in shared memory per tile
+constexpr int kTileNnzCap = 2560;    // CSR entries of a tile's rows staged in shared memory
+
+// Host-side result of the mesh analysis (setup.cpp). All ids internal unless
+// suffixed _user.
+struct HostMesh {
+  int64_t nn = 0, nc = 0, nnz = 0;
+  std::vector<int32_t> n2u, u2n;          // internal->user, user->internal
+  std::vector<double> xy;                 // 2*nn, internal order
+  std::vector<int32_t> cells;             // 3*nc, internal ids, internal cell order
+  std::vector<int32_t> rowptr, colidx;    // P1 pattern == node patches
+  std::vector<int32_t> v2c_ptr;           // nn+1
+  std::vector<uint32_t> v2c_code;         // 3*nc
+  std::vector<int32_t> tile_node;         // ntiles+1
+  std::vector<int32_t> tile_cellptr;      // ntiles+1
+  std::vector<int32_t> tile_cells;        // concatenated cell lists
+  std::vector<uint8_t> is_bnd;            // nn
+  std::vector<int32_t> bnd_user_sorted;   // boundary dofs, user ids ascending
+  int max_row = 0, max_tile_cells = 0, max_tile_nnz = 0;
+};
+
+void analyse_mesh(HostMesh& hm, int64_t nn, int64_t nc, const double* x, int xdim,
+                  const void* cells, int idx_bytes, int order);
+
+// Device view handed to kernels by value.
+struct DevMesh {
+  int64_t nn, nc, nnz;
+  int ntiles;
+  const double2* xy;
+  const int32_t* cells;
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const int32_t* v2c_ptr;
+  const uint32_t* v2c_code;
+  const int32_t* tile_node;
+  const int32_t* tile_cellptr;
+  const int32_t* tile_cells;
+  const uint8_t* is_bc;    // current Dirichlet flags
+};
+
+constexpr int kMaxPartials = 4096;   // >= any reduction grid
+
+struct Matrix {
+  double* vals = nullptr;   // nnz
+  double* dinv = nullptr;   // nn, 1/diag
+  bool valid = false;
+};
+
+struct Launches {  // counters of our own kernel launches
+  int64_t total = 0, spmv = 0, assembly = 0;
+};
+
+}  // namespace cfem
+
+struct cfem_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cfem::HostMesh hm;
+  cfem::DevMesh dm{};
+  // device copies owned by the context
+  std::vector<void*> allocs;
+  int64_t bytes = 0;
+  int32_t *d_n2u = nullptr, *d_u2n = nullptr;
+  uint8_t *d_is_bc = nullptr, *d_is_bnd = nullptr;
+  int32_t* d_bc_nodes = nullptr;  // internal ids, in caller's Dirichlet order
+  int64_t nbc = 0;
+  std::vector<int32_t> bc_user;   // caller's Dirichlet set
+  cfem::Matrix mat[4];
+  // state vectors (internal order)
+  double *uh = nullptr, *u_n = nullptr, *u_old = nullptr, *u_oo = nullptr, *RH = nullptr,
+         *eps = nullptr, *h = nullptr, *g = nullptr, *fluxn = nullptr;
+  double2* w = nullptr;
+  double t = 0.0;
+  // work vectors
+  double *wk[10] = {nullptr};
+  double *stage[4] = {nullptr};   // staging for host<->device + permutation
+  double *partials = nullptr;     // 8 * kMaxPartials doubles
+  double *scalars = nullptr;      // small device scalar block
+  int32_t* status = nullptr;      // device ints: [0]=done flag, [1]=iterations
+  double* h_pinned = nullptr;     // pinned host scratch (small)
+  int32_t* h_status = nullptr;    // pinned
+  // user-order CSR export (lazy)
+  std::vector<int32_t> u_rowptr, u_colidx, u_slot;
+  cfem::Launches launches;
+  int pcg_predict = 8, krylov_predict = 8;
+};

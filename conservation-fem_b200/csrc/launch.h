@@ -1,0 +1,53 @@
+// Host-callable launchers implemented in assembly.cu / linalg.cu / rv.cu.
+// All pointers are device pointers in INTERNAL (Hilbert) numbering.
+#pragma once
+#include "internal.h"
+
+namespace cfem {
+
+// ---- assembly (assembly.cu) --------------------------------------------------
+void launch_mass(cfem_ctx* c, Matrix& M, bool bc);
+void launch_stiffness(cfem_ctx* c, Matrix& K, const double* eps);
+void launch_nodal_h_rhs(cfem_ctx* c, double* b);
+// b = M D_t u + flux(u_n) (zeroed on bc dofs if use_bc); fluxn = flux(u_n) (may be null)
+void launch_rv_rhs(cfem_ctx* c, int flux, int scheme, double dt, const double* u_n,
+                   const double* u_old, const double* u_oo, const double2* w, bool use_bc,
+                   double* b, double* fluxn);
+// F(uh); fluxn (nullable): precomputed nodal flux(u_n) (else recomputed per cell).
+// norm2_partials: per-CTA partial sums of F_i^2 (count returned).
+int launch_cn_residual(cfem_ctx* c, int flux, double dt, const double* uh, const double* u_n,
+                       const double* eps, const double* g, const double* fluxn, double* F,
+                       double* norm2_partials);
+void launch_cn_jacobian(cfem_ctx* c, int flux, double dt, const double* uh, const double* eps,
+                        Matrix& J);
+// A = M + S, b = (M - S) u_n with lifting, S = dt/2 (C_w + K_eps); eps nullable.
+void launch_adv_system(cfem_ctx* c, double dt, const double2* w, const double* eps,
+                       const double* u_n, const double* g, Matrix& A, double* b);
+int assembly_grid(const cfem_ctx* c);
+
+// ---- linear algebra (linalg.cu) ------------------------------------------------
+void launch_spmv(cfem_ctx* c, const Matrix& A, const double* x, double* y);
+void launch_gather(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n);      // dst[i] = src[idx[i]]
+void launch_gather2(cfem_ctx* c, const double2* src, const int32_t* idx, double2* dst, int64_t n);
+void launch_fill(cfem_ctx* c, double* dst, double v, int64_t n);
+void launch_copy(cfem_ctx* c, double* dst, const double* src, int64_t n);
+// x -= dx
+void launch_sub(cfem_ctx* c, double* x, const double* dx, int64_t n);
+struct SolveResult { int iters; double relres; bool converged; };
+SolveResult pcg(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
+                int max_it, int* predict);
+SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol,
+                     double atol, int max_it, int* predict);
+SolveResult gmres(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol,
+                  double atol, int max_it, int* predict);
+double norm2(cfem_ctx* c, const double* v, int64_t n);  // synchronous
+
+// ---- RV (rv.cu) ------------------------------------------------------------------
+// sum / min / max of v -> c->scalars[0..2] (device), no host sync
+void launch_stats(cfem_ctx* c, const double* v);
+void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv, const double* uh,
+                    const double* u_n, double* Rh, const double* h, const double2* w, double* eps);
+void launch_bc_values(cfem_ctx* c, int kind, double value, double t, const double* user_vals,
+                      double* g);
+
+}  // namespace cfem

@@ -1,0 +1,402 @@
+// fp64 CSR SpMV (sub-warp per row, shuffle reduction) and the Jacobi-
+// preconditioned Krylov solvers built on it.  They replace the reference's
+// sparse direct solves: KSP PREONLY + PC LU (Code/Linear_advection/RV_node.py:131-134,
+// Code/Utils/helpers.py:35, dolfinx NewtonSolver default used by Code/KPP/KPP_exact.py:128-154).
+//
+// Design: all Krylov scalars stay on the device.  Dot products are reduced in
+// two fixed-order stages: each CTA writes one partial, every CTA of the NEXT
+// kernel re-reduces the (<= kMaxPartials) partials from L2.  No atomics, so
+// results are bitwise reproducible.  A device-side `done` flag turns the
+// remaining launches of a chunk into no-ops; the host polls it every few
+// iterations (after a predicted iteration count) instead of every iteration.
+#include "device_utils.cuh"
+#include "launch.h"
+
+namespace cfem {
+
+static inline int vec_grid(const cfem_ctx* c, int64_t n) {
+  int64_t b = (n + kBlock - 1) / kBlock;
+  const int64_t cap = (int64_t)c->sm_count * 8;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+#define LAUNCHED(c) do { CUDA_OK(cudaGetLastError()); (c)->launches.total++; } while (0)
+
+// partial slots inside ctx->partials (each kMaxPartials doubles)
+enum { P_PQ = 0, P_RZ0 = 1, P_RZ1 = 2, P_RR = 3, P_BB = 4, P_A = 5, P_B = 6, P_C = 7 };
+// device scalars
+enum { S_SUM = 0, S_MIN = 1, S_MAX = 2, S_BB = 3, S_ALPHA = 4, S_OMEGA = 5, S_RHO = 6, S_RELRES = 7, S_RR = 8 };
+
+// ---------------------------------------------------------------- basic vector kernels
+__global__ void k_gather(const double* __restrict__ src, const int32_t* __restrict__ idx, double* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) dst[i] = src[idx[i]];
+}
+__global__ void k_gather2(const double2* __restrict__ src, const int32_t* __restrict__ idx, double2* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) dst[i] = src[idx[i]];
+}
+__global__ void k_fill(double* __restrict__ dst, double v, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) dst[i] = v;
+}
+__global__ void k_sub(double* __restrict__ x, const double* __restrict__ dx, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) x[i] -= dx[i];
+}
+__global__ void k_norm2(const double* __restrict__ v, int64_t n, double* __restrict__ partials) {
+  __shared__ double red[9];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) s += v[i] * v[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+__global__ void k_sum_partials(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  __shared__ double red[9];
+  const double s = reduce_partials(partials, n, red);
+  if (threadIdx.x == 0) *out = s;
+}
+
+void launch_gather(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n) {
+  k_gather<<<vec_grid(c, n), kBlock, 0, c->stream>>>(src, idx, dst, n); LAUNCHED(c);
+}
+void launch_gather2(cfem_ctx* c, const double2* src, const int32_t* idx, double2* dst, int64_t n) {
+  k_gather2<<<vec_grid(c, n), kBlock, 0, c->stream>>>(src, idx, dst, n); LAUNCHED(c);
+}
+void launch_fill(cfem_ctx* c, double* dst, double v, int64_t n) {
+  k_fill<<<vec_grid(c, n), kBlock, 0, c->stream>>>(dst, v, n); LAUNCHED(c);
+}
+void launch_copy(cfem_ctx* c, double* dst, const double* src, int64_t n) {
+  CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+}
+void launch_sub(cfem_ctx* c, double* x, const double* dx, int64_t n) {
+  k_sub<<<vec_grid(c, n), kBlock, 0, c->stream>>>(x, dx, n); LAUNCHED(c);
+}
+
+double norm2(cfem_ctx* c, const double* v, int64_t n) {
+  const int g = vec_grid(c, n);
+  k_norm2<<<g, kBlock, 0, c->stream>>>(v, n, c->partials + P_C * kMaxPartials); LAUNCHED(c);
+  k_sum_partials<<<1, kBlock, 0, c->stream>>>(c->partials + P_C * kMaxPartials, g, c->scalars + 15); LAUNCHED(c);
+  CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + 15, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return sqrt(c->h_pinned[0]);
+}
+
+// ---------------------------------------------------------------- SpMV
+// LANES lanes cooperate on one row (P1 rows hold ~7 entries, so a warp covers
+// 32/LANES consecutive rows whose CSR entries are contiguous -> coalesced).
+// NDOT fused dot products of y with up to two vectors (d0, d1 == y allowed).
+template <int LANES, int NDOT>
+__global__ void __launch_bounds__(kBlock)
+k_spmv(const int64_t nn, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+       const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+       const double* __restrict__ d0, const double* __restrict__ d1, double* __restrict__ part0,
+       double* __restrict__ part1, const int32_t* __restrict__ status) {
+  if (status && status[0]) return;
+  constexpr int RPW = 32 / LANES;  // rows per warp
+  __shared__ double red[9];
+  const int lane = threadIdx.x & 31, sub = lane / LANES, sl = lane % LANES;
+  const int64_t warp = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int64_t base = warp * RPW; base < nn; base += nwarps * RPW) {
+    const int64_t row = base + sub;
+    double s = 0.0;
+    if (row < nn) {
+      const int p1 = rowptr[row + 1];
+      for (int p = rowptr[row] + sl; p < p1; p += LANES) s += vals[p] * x[colidx[p]];
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (sl == 0 && row < nn) {
+      y[row] = s;
+      if (NDOT >= 1) acc0 += s * (d0 == y ? s : d0[row]);
+      if (NDOT >= 2) acc1 += s * (d1 == y ? s : d1[row]);
+    }
+  }
+  if (NDOT >= 1) {
+    acc0 = block_sum(acc0, red);
+    if (threadIdx.x == 0) part0[blockIdx.x] = acc0;
+  }
+  if (NDOT >= 2) {
+    acc1 = block_sum(acc1, red);
+    if (threadIdx.x == 0) part1[blockIdx.x] = acc1;
+  }
+}
+
+static inline int spmv_grid(const cfem_ctx* c) {
+  const int64_t rows_per_block = (kBlock / 32) * 4;
+  int64_t b = (c->dm.nn + rows_per_block - 1) / rows_per_block;
+  const int64_t cap = (int64_t)c->sm_count * 8;
+  return (int)(b < cap ? b : cap);
+}
+
+template <int NDOT>
+static void spmv_dots(cfem_ctx* c, const Matrix& A, const double* x, double* y, const double* d0,
+                      const double* d1, double* p0, double* p1, bool gated) {
+  k_spmv<8, NDOT><<<spmv_grid(c), kBlock, 0, c->stream>>>(c->dm.nn, c->dm.rowptr, c->dm.colidx, A.vals, x, y, d0,
+                                                          d1, p0, p1, gated ? c->status : nullptr);
+  LAUNCHED(c);
+  c->launches.spmv++;
+}
+
+void launch_spmv(cfem_ctx* c, const Matrix& A, const double* x, double* y) {
+  spmv_dots<0>(c, A, x, y, nullptr, nullptr, nullptr, nullptr, false);
+}
+
+// ---------------------------------------------------------------- PCG
+// r = b - q, z = dinv r, p = z ; partials: rz -> RZ0, rr -> RR, bb -> BB
+__global__ void __launch_bounds__(kBlock)
+k_pcg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q, const double* __restrict__ dinv,
+           double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ part,
+           int32_t* __restrict__ status) {
+  __shared__ double red[9];
+  double rz = 0.0, rr = 0.0, bb = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const double bi = b[i], ri = bi - q[i], zi = dinv[i] * ri;
+    r[i] = ri; z[i] = zi; p[i] = zi;
+    rz += ri * zi; rr += ri * ri; bb += bi * bi;
+  }
+  rz = block_sum(rz, red); rr = block_sum(rr, red); bb = block_sum(bb, red);
+  if (threadIdx.x == 0) {
+    part[P_RZ0 * kMaxPartials + blockIdx.x] = rz;
+    part[P_RR * kMaxPartials + blockIdx.x] = rr;
+    part[P_BB * kMaxPartials + blockIdx.x] = bb;
+    if (blockIdx.x == 0) { status[0] = 0; status[1] = 0; }
+  }
+}
+
+// decides convergence from the partials of the previous kernel (all CTAs agree)
+__global__ void __launch_bounds__(kBlock)
+k_check(const double* __restrict__ part, int npart, double* __restrict__ scalars, int32_t* __restrict__ status,
+        double rtol2, double atol2, int first, int iters_if_stop) {
+  __shared__ double red[9];
+  if (status[0]) return;
+  const double rr = reduce_partials(part + P_RR * kMaxPartials, npart, red);
+  double bb = scalars[S_BB];
+  if (first) bb = reduce_partials(part + P_BB * kMaxPartials, npart, red);
+  if (threadIdx.x == 0) {
+    if (first) scalars[S_BB] = bb;
+    scalars[S_RR] = rr;
+    scalars[S_RELRES] = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
+    if (rr <= rtol2 * bb || rr <= atol2 || !(rr == rr)) {
+      status[0] = (rr == rr) ? 1 : 2;
+      if (iters_if_stop >= 0) status[1] = iters_if_stop;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_pcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ dinv,
+             double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, double* __restrict__ part,
+             int npart_spmv, int npart_vec, int cur, const int32_t* __restrict__ status) {
+  if (status[0]) return;
+  __shared__ double red[9];
+  const double pq = reduce_partials(part + P_PQ * kMaxPartials, npart_spmv, red);
+  const double rz = reduce_partials(part + (cur ? P_RZ1 : P_RZ0) * kMaxPartials, npart_vec, red);
+  const double alpha = rz / pq;
+  double nrz = 0.0, rr = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * q[i], zi = dinv[i] * ri;
+    r[i] = ri; z[i] = zi;
+    nrz += ri * zi; rr += ri * ri;
+  }
+  nrz = block_sum(nrz, red); rr = block_sum(rr, red);
+  if (threadIdx.x == 0) {
+    part[(cur ? P_RZ0 : P_RZ1) * kMaxPartials + blockIdx.x] = nrz;
+    part[P_RR * kMaxPartials + blockIdx.x] = rr;
+  }
+}
+
+// p = z + beta p ; CTA 0 also records the iteration count and tests convergence
+__global__ void __launch_bounds__(kBlock)
+k_pcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ part,
+        int npart_vec, int cur, double* __restrict__ scalars, int32_t* __restrict__ status, double rtol2, double atol2) {
+  if (status[0]) return;
+  __shared__ double red[9];
+  const double rz_old = reduce_partials(part + (cur ? P_RZ1 : P_RZ0) * kMaxPartials, npart_vec, red);
+  const double rz_new = reduce_partials(part + (cur ? P_RZ0 : P_RZ1) * kMaxPartials, npart_vec, red);
+  const double rr = reduce_partials(part + P_RR * kMaxPartials, npart_vec, red);
+  const double bb = scalars[S_BB];
+  const double beta = rz_new / rz_old;
+  const bool stop = rr <= rtol2 * bb || rr <= atol2 || !(rr == rr);
+  if (!stop)
+    for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+      p[i] = z[i] + beta * p[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    status[1] += 1;
+    scalars[S_RR] = rr;
+    scalars[S_RELRES] = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
+    if (stop) status[0] = (rr == rr) ? 1 : 2;
+  }
+}
+
+static bool poll_done(cfem_ctx* c, SolveResult& res) {
+  CUDA_OK(cudaMemcpyAsync(c->h_status, c->status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + S_RELRES, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  res.iters = c->h_status[1];
+  res.relres = c->h_pinned[0];
+  res.converged = c->h_status[0] == 1;
+  return c->h_status[0] != 0;
+}
+
+SolveResult pcg(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
+                int max_it, int* predict) {
+  const int64_t n = c->dm.nn;
+  double *r = c->wk[0], *z = c->wk[1], *p = c->wk[2], *q = c->wk[3];
+  double* part = c->partials;
+  const int gv = vec_grid(c, n), gs = spmv_grid(c);
+  const double rtol2 = rtol * rtol, atol2 = atol * atol;
+  launch_spmv(c, A, x, q);
+  k_pcg_init<<<gv, kBlock, 0, c->stream>>>(n, b, q, A.dinv, r, z, p, part, c->status); LAUNCHED(c);
+  k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c);
+  SolveResult res{0, 0.0, false};
+  int it = 0, next_poll = predict ? (*predict > 2 ? *predict - 1 : 1) : 4;
+  while (it < max_it) {
+    const int cur = it & 1;
+    spmv_dots<1>(c, A, p, q, p, nullptr, part + P_PQ * kMaxPartials, nullptr, true);
+    k_pcg_update<<<gv, kBlock, 0, c->stream>>>(n, p, q, A.dinv, x, r, z, part, gs, gv, cur, c->status); LAUNCHED(c);
+    k_pcg_p<<<gv, kBlock, 0, c->stream>>>(n, z, p, part, gv, cur, c->scalars, c->status, rtol2, atol2); LAUNCHED(c);
+    ++it;
+    if (it >= next_poll || it == max_it) {
+      if (poll_done(c, res)) break;
+      next_poll = it + 3;
+    }
+  }
+  if (!res.converged) poll_done(c, res);
+  if (predict) *predict = res.iters > 0 ? res.iters : 1;
+  return res;
+}
+
+// ---------------------------------------------------------------- BiCGStab (right Jacobi)
+// init: r = b - q ; rhat = r ; p = r ; y = dinv p ; rho = rr
+__global__ void __launch_bounds__(kBlock)
+k_bi_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q, const double* __restrict__ dinv,
+          double* __restrict__ r, double* __restrict__ rhat, double* __restrict__ p, double* __restrict__ y,
+          double* __restrict__ part, int32_t* __restrict__ status) {
+  __shared__ double red[9];
+  double rr = 0.0, bb = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const double bi = b[i], ri = bi - q[i];
+    r[i] = ri; rhat[i] = ri; p[i] = ri; y[i] = dinv[i] * ri;
+    rr += ri * ri; bb += bi * bi;
+  }
+  rr = block_sum(rr, red); bb = block_sum(bb, red);
+  if (threadIdx.x == 0) {
+    part[P_RR * kMaxPartials + blockIdx.x] = rr;
+    part[P_RZ0 * kMaxPartials + blockIdx.x] = rr;  // rho_0 = (rhat, r)
+    part[P_BB * kMaxPartials + blockIdx.x] = bb;
+    if (blockIdx.x == 0) { status[0] = 0; status[1] = 0; }
+  }
+}
+
+// iteration k >= 1: beta = (rho_new/rho_old)(alpha/omega); p = r + beta (p - omega v); y = dinv p
+__global__ void __launch_bounds__(kBlock)
+k_bi_p(int64_t n, const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
+       double* __restrict__ p, double* __restrict__ y, const double* __restrict__ part, int npart, int cur,
+       double* __restrict__ scalars, int32_t* __restrict__ status, double rtol2, double atol2) {
+  if (status[0]) return;
+  __shared__ double red[9];
+  const double rho_old = reduce_partials(part + (cur ? P_RZ0 : P_RZ1) * kMaxPartials, npart, red);
+  const double rho_new = reduce_partials(part + (cur ? P_RZ1 : P_RZ0) * kMaxPartials, npart, red);
+  const double rr = reduce_partials(part + P_RR * kMaxPartials, npart, red);
+  const double bb = scalars[S_BB], alpha = scalars[S_ALPHA], omega = scalars[S_OMEGA];
+  const bool stop = rr <= rtol2 * bb || rr <= atol2 || !(rr == rr);
+  if (!stop) {
+    const double beta = (rho_new / rho_old) * (alpha / omega);
+    for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+      const double pi = r[i] + beta * (p[i] - omega * v[i]);
+      p[i] = pi; y[i] = dinv[i] * pi;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    status[1] += 1;
+    scalars[S_RR] = rr;
+    scalars[S_RELRES] = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
+    if (stop) status[0] = (rr == rr) ? 1 : 2;
+  }
+}
+
+// alpha = rho / (rhat, v) ; s = r - alpha v ; z = dinv s
+__global__ void __launch_bounds__(kBlock)
+k_bi_s(int64_t n, const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
+       double* __restrict__ s, double* __restrict__ z, const double* __restrict__ part, int npart_vec,
+       int npart_spmv, int cur, double* __restrict__ scalars, const int32_t* __restrict__ status) {
+  if (status[0]) return;
+  __shared__ double red[9];
+  const double rho = reduce_partials(part + (cur ? P_RZ1 : P_RZ0) * kMaxPartials, npart_vec, red);
+  const double rv = reduce_partials(part + P_PQ * kMaxPartials, npart_spmv, red);
+  const double alpha = rv != 0.0 ? rho / rv : 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const double si = r[i] - alpha * v[i];
+    s[i] = si; z[i] = dinv[i] * si;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) scalars[S_ALPHA] = alpha;
+}
+
+// omega = (t,s)/(t,t) ; x += alpha y + omega z ; r = s - omega t ; rho' = (rhat, r), rr
+__global__ void __launch_bounds__(kBlock)
+k_bi_x(int64_t n, const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ s,
+       const double* __restrict__ t, const double* __restrict__ rhat, double* __restrict__ x, double* __restrict__ r,
+       double* __restrict__ part, int npart_spmv, int cur, double* __restrict__ scalars,
+       const int32_t* __restrict__ status) {
+  if (status[0]) return;
+  __shared__ double red[9];
+  const double ts = reduce_partials(part + P_A * kMaxPartials, npart_spmv, red);
+  const double tt = reduce_partials(part + P_B * kMaxPartials, npart_spmv, red);
+  const double omega = tt > 0.0 ? ts / tt : 0.0;
+  const double alpha = scalars[S_ALPHA];
+  double rho = 0.0, rr = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    x[i] += alpha * y[i] + omega * z[i];
+    const double ri = s[i] - omega * t[i];
+    r[i] = ri;
+    rho += rhat[i] * ri; rr += ri * ri;
+  }
+  rho = block_sum(rho, red); rr = block_sum(rr, red);
+  if (threadIdx.x == 0) {
+    part[(cur ? P_RZ0 : P_RZ1) * kMaxPartials + blockIdx.x] = rho;
+    part[P_RR * kMaxPartials + blockIdx.x] = rr;
+    if (blockIdx.x == 0) scalars[S_OMEGA] = omega;
+  }
+}
+
+SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
+                     int max_it, int* predict) {
+  const int64_t n = c->dm.nn;
+  double *r = c->wk[0], *rhat = c->wk[1], *p = c->wk[2], *v = c->wk[3], *s = c->wk[4], *t = c->wk[5],
+         *y = c->wk[6], *z = c->wk[7];
+  double* part = c->partials;
+  const int gv = vec_grid(c, n), gs = spmv_grid(c);
+  const double rtol2 = rtol * rtol, atol2 = atol * atol;
+  launch_spmv(c, A, x, v);
+  k_bi_init<<<gv, kBlock, 0, c->stream>>>(n, b, v, A.dinv, r, rhat, p, y, part, c->status); LAUNCHED(c);
+  k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c);
+  SolveResult res{0, 0.0, false};
+  int it = 0, next_poll = predict ? (*predict > 2 ? *predict - 1 : 1) : 4;
+  while (it < max_it) {
+    const int cur = it & 1;  // rho of this iteration lives in RZ[cur]
+    if (it > 0) {
+      k_bi_p<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, p, y, part, gv, cur, c->scalars, c->status, rtol2, atol2);
+      LAUNCHED(c);
+    }
+    spmv_dots<1>(c, A, y, v, rhat, nullptr, part + P_PQ * kMaxPartials, nullptr, true);
+    k_bi_s<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, s, z, part, gv, gs, cur, c->scalars, c->status); LAUNCHED(c);
+    spmv_dots<2>(c, A, z, t, s, t, part + P_A * kMaxPartials, part + P_B * kMaxPartials, true);
+    k_bi_x<<<gv, kBlock, 0, c->stream>>>(n, y, z, s, t, rhat, x, r, part, gs, cur, c->scalars, c->status); LAUNCHED(c);
+    ++it;
+    if (it >= next_poll || it == max_it) {
+      // the convergence test for iteration `it` runs inside the next k_bi_p; issue a stand-alone check
+      k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 0, it); LAUNCHED(c);
+      if (poll_done(c, res)) break;
+      next_poll = it + 2;
+    }
+  }
+  if (!res.converged) { poll_done(c, res); }
+  if (predict) *predict = res.iters > 0 ? res.iters : 1;
+  return res;
+}
+
+SolveResult gmres(cfem_ctx*, const Matrix&, const double*, double*, double, double, int, int*) {
+  CFEM_THROW(-4, "GMRES is not built yet; use CFEM_SOLVER_BICGSTAB");
+}
+
+}  // namespace cfem

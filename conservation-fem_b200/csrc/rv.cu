@@ -1,0 +1,259 @@
+// Fused residual-viscosity kernels: global sum/min/max of a nodal field (one
+// pass, fixed-order two-stage reduction), the patch max/min + epsilon kernel
+// (sub-warp per node, shuffle reductions over the node's CSR row == its patch),
+// and the Dirichlet-value kernel.
+//
+// Restates the per-node Python loops of the reference, Code/Utils/RV.py:27-142.
+#include "device_utils.cuh"
+#include "launch.h"
+
+namespace cfem {
+
+#define LAUNCHED(c) do { CUDA_OK(cudaGetLastError()); (c)->launches.total++; } while (0)
+
+static inline int vec_grid(const cfem_ctx* c, int64_t n) {
+  int64_t b = (n + kBlock - 1) / kBlock;
+  const int64_t cap = (int64_t)c->sm_count * 8;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+enum { P_SUM = 5, P_MIN = 6, P_MAX = 7 };  // partial slots (shared with linalg.cu's P_A..P_C)
+
+// ||f'(u)||_2 with the operation order of np.linalg.norm(np.array(f'(u)))
+template <int FLUX>
+__device__ __forceinline__ double beta_of(double u) {
+  if (FLUX == CFEM_FLUX_BURGERS) return sqrt(__dadd_rn(__dmul_rn(u, u), __dmul_rn(u, u)));
+  double s, c;
+  sincos(u, &s, &c);
+  return sqrt(__dadd_rn(__dmul_rn(c, c), __dmul_rn(s, s)));
+}
+
+// one pass: partial sum / min / max of v; optionally beta[i] = ||f'(v_i)||
+template <int FLUX>
+__global__ void __launch_bounds__(kBlock)
+k_stats(int64_t n, const double* __restrict__ v, double* __restrict__ beta, double* __restrict__ part) {
+  __shared__ double red[9];
+  double s = 0.0, mn = INFINITY, mx = -INFINITY;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const double x = v[i];
+    s += x; mn = fmin(mn, x); mx = fmax(mx, x);
+    if (FLUX >= 0) beta[i] = beta_of<FLUX>(x);
+  }
+  s = block_sum(s, red); mn = block_min(mn, red); mx = block_max(mx, red);
+  if (threadIdx.x == 0) {
+    part[P_SUM * kMaxPartials + blockIdx.x] = s;
+    part[P_MIN * kMaxPartials + blockIdx.x] = mn;
+    part[P_MAX * kMaxPartials + blockIdx.x] = mx;
+  }
+}
+
+// ||v - mean(v)||_inf from the partials (np.linalg.norm(u - np.mean(u), ord=inf), RV.py:59)
+__device__ __forceinline__ double absolute_term(const double* part, int npart, int64_t n, double* red) {
+  double s = 0.0, mn = INFINITY, mx = -INFINITY;
+  for (int i = threadIdx.x; i < npart; i += kBlock) {
+    s += part[P_SUM * kMaxPartials + i];
+    mn = fmin(mn, part[P_MIN * kMaxPartials + i]);
+    mx = fmax(mx, part[P_MAX * kMaxPartials + i]);
+  }
+  s = block_sum(s, red); mn = block_min(mn, red); mx = block_max(mx, red);
+  const double mean = s / (double)n;
+  return fmax(fabs(mx - mean), fabs(mn - mean));
+}
+
+// Python min(a, b): b if b < a else a  (NaN / inf second argument keeps a)
+__device__ __forceinline__ double pymin(double a, double b) { return b < a ? b : a; }
+
+// RV.get_epsilon_nonlinear (RV.py:56-90) / get_epsilon_linear (RV.py:92-127)
+template <int LANES, bool LINEAR>
+__global__ void __launch_bounds__(kBlock)
+k_epsilon_patch(const int64_t nn, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                const double* __restrict__ u_n, const double* __restrict__ Rh, const double* __restrict__ beta,
+                const double2* __restrict__ w, const double* __restrict__ h, const double* __restrict__ part,
+                int npart, double Cvel, double Crv, double* __restrict__ eps) {
+  __shared__ double red[9];
+  const double A = absolute_term(part, npart, nn, red);
+  constexpr int RPW = 32 / LANES;
+  const int lane = threadIdx.x & 31, sub = lane / LANES, sl = lane % LANES;
+  const int64_t warp = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
+  for (int64_t base = warp * RPW; base < nn; base += nwarps * RPW) {
+    const int64_t row = base + sub;
+    double umax = -INFINITY, umin = INFINITY, rmax = 0.0, bmax = 0.0;
+    if (row < nn) {
+      const int p1 = rowptr[row + 1];
+      for (int p = rowptr[row] + sl; p < p1; p += LANES) {
+        const int j = colidx[p];
+        const double uj = u_n[j];
+        umax = fmax(umax, uj); umin = fmin(umin, uj);
+        rmax = fmax(rmax, fabs(Rh[j]));
+        if (!LINEAR) bmax = fmax(bmax, beta[j]);
+      }
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+      umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+      umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+      rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+      if (!LINEAR) bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+    }
+    if (sl == 0 && row < nn) {
+      if (LINEAR) {
+        const double2 wi = w[row];  // centre node, RV.py:113-115
+        bmax = sqrt(__dadd_rn(__dmul_rn(wi.x, wi.x), __dmul_rn(wi.y, wi.y)));
+      }
+      const double hi = h[row];
+      const double n_i = fabs((umax - umin) - A);
+      const double Ri = rmax / n_i;
+      const double first = __dmul_rn(__dmul_rn(Cvel, hi), bmax);
+      const double second = __dmul_rn(__dmul_rn(Crv, __dmul_rn(hi, hi)), fabs(Ri));
+      eps[row] = pymin(first, second);
+    }
+  }
+}
+
+// pointwise variants: RV.get_epsilon (RV.py:27-40), get_epsilon_1storder (RV.py:42-54),
+// get_epsilon_linear_simple (RV.py:129-142; also normalises Rh in place)
+template <int FLUX>
+__global__ void __launch_bounds__(kBlock)
+k_epsilon_pointwise(int64_t n, int variant, const double* __restrict__ uh, double* __restrict__ Rh,
+                    const double* __restrict__ h, const double2* __restrict__ w, const double* __restrict__ part,
+                    int npart, double Cvel, double Crv, double* __restrict__ eps) {
+  __shared__ double red[9];
+  double A = 1.0;
+  if (variant == CFEM_EPS_LINEAR_SIMPLE) A = absolute_term(part, npart, n, red);
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    double b;
+    if (FLUX == CFEM_FLUX_ADVECTION) {
+      const double2 wi = w[i];
+      b = sqrt(__dadd_rn(__dmul_rn(wi.x, wi.x), __dmul_rn(wi.y, wi.y)));
+    } else {
+      b = beta_of<FLUX == CFEM_FLUX_ADVECTION ? CFEM_FLUX_BURGERS : FLUX>(uh[i]);
+    }
+    const double hi = h[i];
+    if (variant == CFEM_EPS_FIRST_ORDER) {
+      eps[i] = __dmul_rn(__dmul_rn(0.5, hi), b);
+    } else {
+      double r = Rh[i];
+      if (variant == CFEM_EPS_LINEAR_SIMPLE) { r = r / A; Rh[i] = r; }
+      eps[i] = pymin(__dmul_rn(__dmul_rn(Cvel, hi), b), __dmul_rn(__dmul_rn(Crv, __dmul_rn(hi, hi)), fabs(r)));
+    }
+  }
+}
+
+void launch_stats(cfem_ctx* c, const double* v) {
+  k_stats<-1><<<vec_grid(c, c->dm.nn), kBlock, 0, c->stream>>>(c->dm.nn, v, nullptr, c->partials); LAUNCHED(c);
+}
+
+void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv, const double* uh,
+                    const double* u_n, double* Rh, const double* h, const double2* w, double* eps) {
+  const int64_t n = c->dm.nn;
+  const int gv = vec_grid(c, n);
+  if (!h) CFEM_THROW(-1, "rv_epsilon: nodal mesh size h is required");
+  if (variant == CFEM_EPS_NONLINEAR || variant == CFEM_EPS_LINEAR) {
+    if (!uh || !u_n || !Rh) CFEM_THROW(-1, "rv_epsilon: uh, u_n and Rh are required");
+    double* beta = c->wk[9];
+    if (variant == CFEM_EPS_LINEAR) {
+      if (!w) CFEM_THROW(-1, "rv_epsilon(linear): velocity field w is required");
+      k_stats<-1><<<gv, kBlock, 0, c->stream>>>(n, uh, nullptr, c->partials);
+    } else if (flux == CFEM_FLUX_BURGERS) {
+      k_stats<CFEM_FLUX_BURGERS><<<gv, kBlock, 0, c->stream>>>(n, uh, beta, c->partials);
+    } else if (flux == CFEM_FLUX_KPP) {
+      k_stats<CFEM_FLUX_KPP><<<gv, kBlock, 0, c->stream>>>(n, uh, beta, c->partials);
+    } else {
+      CFEM_THROW(-1, "rv_epsilon(nonlinear): flux must be BURGERS or KPP");
+    }
+    LAUNCHED(c);
+    const int64_t rows_per_block = (kBlock / 32) * 4;
+    int64_t g = (n + rows_per_block - 1) / rows_per_block;
+    const int64_t cap = (int64_t)c->sm_count * 8;
+    if (g > cap) g = cap;
+    if (variant == CFEM_EPS_LINEAR)
+      k_epsilon_patch<8, true><<<(int)g, kBlock, 0, c->stream>>>(n, c->dm.rowptr, c->dm.colidx, u_n, Rh, nullptr, w, h,
+                                                               c->partials, gv, Cvel, Crv, eps);
+    else
+      k_epsilon_patch<8, false><<<(int)g, kBlock, 0, c->stream>>>(n, c->dm.rowptr, c->dm.colidx, u_n, Rh, beta, w, h,
+                                                                c->partials, gv, Cvel, Crv, eps);
+    LAUNCHED(c);
+    return;
+  }
+  if (variant == CFEM_EPS_POINTWISE || variant == CFEM_EPS_FIRST_ORDER || variant == CFEM_EPS_LINEAR_SIMPLE) {
+    if (variant != CFEM_EPS_FIRST_ORDER && !Rh) CFEM_THROW(-1, "rv_epsilon: residual is required");
+    if (variant == CFEM_EPS_LINEAR_SIMPLE) {
+      if (!u_n) CFEM_THROW(-1, "rv_epsilon(linear_simple): u_n is required");
+      flux = CFEM_FLUX_ADVECTION;
+      k_stats<-1><<<gv, kBlock, 0, c->stream>>>(n, u_n, nullptr, c->partials); LAUNCHED(c);
+    }
+    if (flux == CFEM_FLUX_ADVECTION) {
+      if (!w) CFEM_THROW(-1, "rv_epsilon: velocity field w is required");
+      k_epsilon_pointwise<CFEM_FLUX_ADVECTION><<<gv, kBlock, 0, c->stream>>>(n, variant, uh, Rh, h, w, c->partials, gv, Cvel, Crv, eps);
+    } else if (flux == CFEM_FLUX_BURGERS) {
+      if (!uh) CFEM_THROW(-1, "rv_epsilon: uh is required");
+      k_epsilon_pointwise<CFEM_FLUX_BURGERS><<<gv, kBlock, 0, c->stream>>>(n, variant, uh, Rh, h, w, c->partials, gv, Cvel, Crv, eps);
+    } else if (flux == CFEM_FLUX_KPP) {
+      if (!uh) CFEM_THROW(-1, "rv_epsilon: uh is required");
+      k_epsilon_pointwise<CFEM_FLUX_KPP><<<gv, kBlock, 0, c->stream>>>(n, variant, uh, Rh, h, w, c->partials, gv, Cvel, Crv, eps);
+    } else {
+      CFEM_THROW(-1, "rv_epsilon: unknown flux");
+    }
+    LAUNCHED(c);
+    return;
+  }
+  CFEM_THROW(-1, "rv_epsilon: unknown variant");
+}
+
+// ---------------------------------------------------------------- Dirichlet data
+// Exact solution of the 2-D Burgers Riemann problem, same branch order and
+// operation order as the reference (Code/Burgers_equation/Exact_Burger_RV.py:37-66),
+// unfused arithmetic so that nodes lying on a front classify identically.
+__device__ double burgers_exact(double X, double Y, double t) {
+  const double half = 0.5;
+  double u = 0.0;
+  const double a1 = __dsub_rn(half, __ddiv_rn(__dmul_rn(3.0, t), 5.0));   // 1/2 - 3t/5
+  const double y1 = __dadd_rn(half, __ddiv_rn(__dmul_rn(3.0, t), 20.0));  // 1/2 + 3t/20
+  const bool m1 = X <= a1;
+  if (m1 && Y > y1) u = -0.2;
+  if (m1 && Y <= y1) u = 0.5;
+  const double a2 = __dsub_rn(half, __ddiv_rn(t, 4.0));                   // 1/2 - t/4
+  const bool m2 = (a1 <= X) && (X <= a2);
+  const double l2 = __dsub_rn(__dadd_rn(__ddiv_rn(__dmul_rn(-8.0, X), 7.0), 15.0 / 14.0),
+                              __ddiv_rn(__dmul_rn(15.0, t), 28.0));
+  if (m2 && Y > l2) u = -1.0;
+  if (m2 && Y <= l2) u = 0.5;
+  const double a3 = __dadd_rn(half, __ddiv_rn(t, 2.0));                   // 1/2 + t/2
+  const bool m3 = (a2 <= X) && (X <= a3);
+  const double l3 = __dsub_rn(__dadd_rn(__ddiv_rn(X, 6.0), 5.0 / 12.0), __ddiv_rn(__dmul_rn(5.0, t), 24.0));
+  if (m3 && Y > l3) u = -1.0;
+  if (m3 && Y <= l3) u = 0.5;
+  const double a4 = __dadd_rn(half, __ddiv_rn(__dmul_rn(4.0, t), 5.0));   // 1/2 + 4t/5
+  const bool m4 = (a3 <= X) && (X <= a4);
+  const double q = __dsub_rn(__dadd_rn(X, t), half);
+  const double l4 = __dsub_rn(X, __dmul_rn(__ddiv_rn(5.0, __dmul_rn(18.0, t)), __dmul_rn(q, q)));
+  if (m4 && Y > l4) u = -1.0;
+  if (m4 && Y <= l4) u = __ddiv_rn(__dsub_rn(__dmul_rn(2.0, X), 1.0), __dmul_rn(2.0, t));
+  const bool m5 = X >= a4;
+  const double y5 = __dsub_rn(half, __ddiv_rn(t, 10.0));
+  if (m5 && Y > y5) u = -1.0;
+  if (m5 && Y <= y5) u = 0.8;
+  return u;
+}
+
+__global__ void k_bc_values(int64_t nbc, const int32_t* __restrict__ bc_nodes, int kind, double value, double t,
+                            const double* __restrict__ user, const double2* __restrict__ xy, double* __restrict__ g) {
+  for (int64_t j = blockIdx.x * (int64_t)kBlock + threadIdx.x; j < nbc; j += (int64_t)gridDim.x * kBlock) {
+    const int node = bc_nodes[j];
+    double v;
+    if (kind == CFEM_BC_CONSTANT) v = value;
+    else if (kind == CFEM_BC_USER) v = user[j];
+    else { const double2 p = xy[node]; v = burgers_exact(p.x, p.y, t); }
+    g[node] = v;
+  }
+}
+
+void launch_bc_values(cfem_ctx* c, int kind, double value, double t, const double* user_vals, double* g) {
+  if (c->nbc == 0) return;
+  if (kind == CFEM_BC_USER && !user_vals) CFEM_THROW(-1, "CFEM_BC_USER needs bc_values");
+  k_bc_values<<<vec_grid(c, c->nbc), kBlock, 0, c->stream>>>(c->nbc, c->d_bc_nodes, kind, value, t, user_vals, c->dm.xy, g);
+  LAUNCHED(c);
+}
+
+}  // namespace cfem
