@@ -50,7 +50,7 @@ class StepStats(C.Structure):
         ("steps", C.c_int64), ("newton_iterations", C.c_int64), ("mass_iterations", C.c_int64),
         ("krylov_iterations", C.c_int64), ("spmv_launches", C.c_int64),
         ("assembly_launches", C.c_int64), ("kernel_launches", C.c_int64),
-        ("last_newton_residual", C.c_double), ("time", C.c_double),
+        ("last_newton_residual", C.c_double), ("time", C.c_double), ("device_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -95,6 +95,8 @@ SIGNATURES = {
     "cfem_state_get": (_I, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(_D)]),
     "cfem_step_scalar": (_I, [_P, C.POINTER(StepParams), _I, _P, C.POINTER(StepStats)]),
     "cfem_step_advection": (_I, [_P, C.POINTER(StepParams), _I, _I, C.POINTER(StepStats)]),
+    "cfem_profile_begin": (_I, [_P, _I]),
+    "cfem_profile_end": (_I, [_P, C.POINTER(_D), C.POINTER(_L)]),
     "cfem_time_kernel": (_I, [_P, _I, _I, _I, C.POINTER(_D), C.POINTER(_D)]),
     "cfem_host_analyse": (_I, [C.POINTER(_P), _L, _L, _P, _I, _P, _I, _I]),
     "cfem_host_size": (_L, [_P, _I]),

@@ -13,6 +13,20 @@ using namespace cfem;
 namespace cfem {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
+
+ProfScope::ProfScope(cfem_ctx* c_, int cat) : c(c_), active(false) {
+  Profiler& p = c->prof;
+  if (!p.on || p.used + 2 > p.ev.size()) return;
+  active = true;
+  p.cat[p.used / 2] = cat;
+  cudaEventRecord(p.ev[p.used], c->stream);
+}
+ProfScope::~ProfScope() {
+  if (!active) return;
+  Profiler& p = c->prof;
+  cudaEventRecord(p.ev[p.used + 1], c->stream);
+  p.used += 2;
+}
 }  // namespace cfem
 
 #define API_BEGIN try {
@@ -244,6 +258,7 @@ void cfem_destroy(cfem_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (void* p : c->allocs) cudaFree(p);
+  for (cudaEvent_t e : c->prof.ev) cudaEventDestroy(e);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -491,6 +506,10 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
   const int64_t nn = c->dm.nn;
   const Launches l0 = c->launches;
   cfem_step_stats st{};
+  cudaEvent_t ev0, ev1;
+  CUDA_OK(cudaEventCreate(&ev0));
+  CUDA_OK(cudaEventCreate(&ev1));
+  CUDA_OK(cudaEventRecord(ev0, c->stream));
   const double* d_bc_user = nullptr;
   if (p->bc_kind == CFEM_BC_USER) {
     if (!bc_values) CFEM_THROW(-1, "step_scalar: CFEM_BC_USER needs bc_values");
@@ -545,6 +564,11 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
     launch_copy(c, c->u_n, c->uh, nn);
     st.steps++;
   }
+  CUDA_OK(cudaEventRecord(ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(ev1));
+  { float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); st.device_ms = ms; }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
   CUDA_OK(cudaStreamSynchronize(c->stream));
   st.time = c->t;
   st.kernel_launches = c->launches.total - l0.total;
@@ -563,6 +587,10 @@ int cfem_step_advection(cfem_ctx* c, const cfem_step_params* p, int n_steps, int
   const int64_t nn = c->dm.nn;
   const Launches l0 = c->launches;
   cfem_step_stats st{};
+  cudaEvent_t ev0, ev1;
+  CUDA_OK(cudaEventCreate(&ev0));
+  CUDA_OK(cudaEventCreate(&ev1));
+  CUDA_OK(cudaEventRecord(ev0, c->stream));
   double* b = c->wk[8];
   Matrix& A = c->mat[CFEM_MAT_SYSTEM];
   launch_bc_values(c, CFEM_BC_CONSTANT, p->bc_kind == CFEM_BC_CONSTANT ? p->bc_value : 0.0, 0.0, nullptr, c->g);
@@ -594,12 +622,50 @@ int cfem_step_advection(cfem_ctx* c, const cfem_step_params* p, int n_steps, int
     }
     st.steps++;
   }
+  CUDA_OK(cudaEventRecord(ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(ev1));
+  { float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); st.device_ms = ms; }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
   CUDA_OK(cudaStreamSynchronize(c->stream));
   st.time = c->t;
   st.kernel_launches = c->launches.total - l0.total;
   st.spmv_launches = c->launches.spmv - l0.spmv;
   st.assembly_launches = c->launches.assembly - l0.assembly;
   if (stats) *stats = st;
+  API_END
+}
+
+int cfem_profile_begin(cfem_ctx* c, int max_launches) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  Profiler& p = c->prof;
+  if (max_launches < 16) max_launches = 16;
+  while (p.ev.size() < (size_t)2 * max_launches) {
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreate(&e));
+    p.ev.push_back(e);
+  }
+  p.cat.assign(p.ev.size() / 2, 0);
+  p.used = 0;
+  p.on = true;
+  API_END
+}
+
+int cfem_profile_end(cfem_ctx* c, double* ms_per_category, int64_t* launches_per_category) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  Profiler& p = c->prof;
+  p.on = false;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < PROF_NCAT; ++k) { ms_per_category[k] = 0.0; launches_per_category[k] = 0; }
+  for (size_t e = 0; e + 1 < p.used; e += 2) {
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, p.ev[e], p.ev[e + 1]));
+    ms_per_category[p.cat[e / 2]] += ms;
+    launches_per_category[p.cat[e / 2]] += 1;
+  }
+  p.used = 0;
   API_END
 }
 

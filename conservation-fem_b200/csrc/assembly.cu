@@ -438,6 +438,7 @@ static void run_tiles(cfem_ctx* c, const Op& op, bool bc, double* vals, double* 
     CUDA_OK(cudaFuncSetAttribute(k_tile_assemble<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
+  ProfScope ps(c, Op::MAT ? PROF_ASM_MAT : PROF_ASM_VEC);
   k_tile_assemble<Op><<<assembly_grid(c), kTileNodes, smem, c->stream>>>(c->dm, op, bc, vals, dinv, partials, ccap, nnzcap);
   CUDA_OK(cudaGetLastError());
   c->launches.total++;

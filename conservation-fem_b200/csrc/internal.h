@@ -82,6 +82,25 @@ struct Launches {  // counters of our own kernel launches
   int64_t total = 0, spmv = 0, assembly = 0;
 };
 
+// Optional per-launch CUDA-event bracketing (bench.py roofline leg).
+enum { PROF_SPMV = 0, PROF_ASM_VEC = 1, PROF_ASM_MAT = 2, PROF_KRYLOV_VEC = 3, PROF_RV = 4, PROF_MISC = 5, PROF_NCAT = 8 };
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  std::vector<int> cat;
+  size_t used = 0;               // events used
+};
+
+}  // namespace cfem
+
+struct cfem_ctx;
+namespace cfem {
+// RAII: brackets the launches issued inside its scope with two events when profiling is on.
+struct ProfScope {
+  cfem_ctx* c; bool active;
+  ProfScope(cfem_ctx* c, int cat);
+  ~ProfScope();
+};
 }  // namespace cfem
 
 struct cfem_ctx {
@@ -115,5 +134,6 @@ struct cfem_ctx {
   // user-order CSR export (lazy)
   std::vector<int32_t> u_rowptr, u_colidx, u_slot;
   cfem::Launches launches;
+  cfem::Profiler prof;
   int pcg_predict = 8, krylov_predict = 8;
 };

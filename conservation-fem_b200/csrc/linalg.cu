@@ -54,18 +54,22 @@ __global__ void k_sum_partials(const double* __restrict__ partials, int n, doubl
 }
 
 void launch_gather(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n) {
+  ProfScope ps(c, PROF_MISC);
   k_gather<<<vec_grid(c, n), kBlock, 0, c->stream>>>(src, idx, dst, n); LAUNCHED(c);
 }
 void launch_gather2(cfem_ctx* c, const double2* src, const int32_t* idx, double2* dst, int64_t n) {
+  ProfScope ps(c, PROF_MISC);
   k_gather2<<<vec_grid(c, n), kBlock, 0, c->stream>>>(src, idx, dst, n); LAUNCHED(c);
 }
 void launch_fill(cfem_ctx* c, double* dst, double v, int64_t n) {
+  ProfScope ps(c, PROF_MISC);
   k_fill<<<vec_grid(c, n), kBlock, 0, c->stream>>>(dst, v, n); LAUNCHED(c);
 }
 void launch_copy(cfem_ctx* c, double* dst, const double* src, int64_t n) {
   CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
 }
 void launch_sub(cfem_ctx* c, double* x, const double* dx, int64_t n) {
+  ProfScope ps(c, PROF_MISC);
   k_sub<<<vec_grid(c, n), kBlock, 0, c->stream>>>(x, dx, n); LAUNCHED(c);
 }
 
@@ -130,6 +134,7 @@ static inline int spmv_grid(const cfem_ctx* c) {
 template <int NDOT>
 static void spmv_dots(cfem_ctx* c, const Matrix& A, const double* x, double* y, const double* d0,
                       const double* d1, double* p0, double* p1, bool gated) {
+  ProfScope ps(c, PROF_SPMV);
   k_spmv<8, NDOT><<<spmv_grid(c), kBlock, 0, c->stream>>>(c->dm.nn, c->dm.rowptr, c->dm.colidx, A.vals, x, y, d0,
                                                           d1, p0, p1, gated ? c->status : nullptr);
   LAUNCHED(c);
@@ -246,15 +251,15 @@ SolveResult pcg(cfem_ctx* c, const Matrix& A, const double* b, double* x, double
   const int gv = vec_grid(c, n), gs = spmv_grid(c);
   const double rtol2 = rtol * rtol, atol2 = atol * atol;
   launch_spmv(c, A, x, q);
-  k_pcg_init<<<gv, kBlock, 0, c->stream>>>(n, b, q, A.dinv, r, z, p, part, c->status); LAUNCHED(c);
-  k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c);
+  { ProfScope ps(c, PROF_KRYLOV_VEC); k_pcg_init<<<gv, kBlock, 0, c->stream>>>(n, b, q, A.dinv, r, z, p, part, c->status); LAUNCHED(c); }
+  { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
   SolveResult res{0, 0.0, false};
   int it = 0, next_poll = predict ? (*predict > 2 ? *predict - 1 : 1) : 4;
   while (it < max_it) {
     const int cur = it & 1;
     spmv_dots<1>(c, A, p, q, p, nullptr, part + P_PQ * kMaxPartials, nullptr, true);
-    k_pcg_update<<<gv, kBlock, 0, c->stream>>>(n, p, q, A.dinv, x, r, z, part, gs, gv, cur, c->status); LAUNCHED(c);
-    k_pcg_p<<<gv, kBlock, 0, c->stream>>>(n, z, p, part, gv, cur, c->scalars, c->status, rtol2, atol2); LAUNCHED(c);
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_pcg_update<<<gv, kBlock, 0, c->stream>>>(n, p, q, A.dinv, x, r, z, part, gs, gv, cur, c->status); LAUNCHED(c); }
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_pcg_p<<<gv, kBlock, 0, c->stream>>>(n, z, p, part, gv, cur, c->scalars, c->status, rtol2, atol2); LAUNCHED(c); }
     ++it;
     if (it >= next_poll || it == max_it) {
       if (poll_done(c, res)) break;
@@ -368,24 +373,24 @@ SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, d
   const int gv = vec_grid(c, n), gs = spmv_grid(c);
   const double rtol2 = rtol * rtol, atol2 = atol * atol;
   launch_spmv(c, A, x, v);
-  k_bi_init<<<gv, kBlock, 0, c->stream>>>(n, b, v, A.dinv, r, rhat, p, y, part, c->status); LAUNCHED(c);
-  k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c);
+  { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_init<<<gv, kBlock, 0, c->stream>>>(n, b, v, A.dinv, r, rhat, p, y, part, c->status); LAUNCHED(c); }
+  { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
   SolveResult res{0, 0.0, false};
   int it = 0, next_poll = predict ? (*predict > 2 ? *predict - 1 : 1) : 4;
   while (it < max_it) {
     const int cur = it & 1;  // rho of this iteration lives in RZ[cur]
     if (it > 0) {
-      k_bi_p<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, p, y, part, gv, cur, c->scalars, c->status, rtol2, atol2);
-      LAUNCHED(c);
+      { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_p<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, p, y, part, gv, cur, c->scalars, c->status, rtol2, atol2);
+      LAUNCHED(c); }
     }
     spmv_dots<1>(c, A, y, v, rhat, nullptr, part + P_PQ * kMaxPartials, nullptr, true);
-    k_bi_s<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, s, z, part, gv, gs, cur, c->scalars, c->status); LAUNCHED(c);
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_s<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, s, z, part, gv, gs, cur, c->scalars, c->status); LAUNCHED(c); }
     spmv_dots<2>(c, A, z, t, s, t, part + P_A * kMaxPartials, part + P_B * kMaxPartials, true);
-    k_bi_x<<<gv, kBlock, 0, c->stream>>>(n, y, z, s, t, rhat, x, r, part, gs, cur, c->scalars, c->status); LAUNCHED(c);
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_x<<<gv, kBlock, 0, c->stream>>>(n, y, z, s, t, rhat, x, r, part, gs, cur, c->scalars, c->status); LAUNCHED(c); }
     ++it;
     if (it >= next_poll || it == max_it) {
       // the convergence test for iteration `it` runs inside the next k_bi_p; issue a stand-alone check
-      k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 0, it); LAUNCHED(c);
+      { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 0, it); LAUNCHED(c); }
       if (poll_done(c, res)) break;
       next_poll = it + 2;
     }

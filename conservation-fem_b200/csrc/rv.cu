@@ -146,6 +146,7 @@ void launch_stats(cfem_ctx* c, const double* v) {
 
 void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv, const double* uh,
                     const double* u_n, double* Rh, const double* h, const double2* w, double* eps) {
+  ProfScope ps(c, PROF_RV);
   const int64_t n = c->dm.nn;
   const int gv = vec_grid(c, n);
   if (!h) CFEM_THROW(-1, "rv_epsilon: nodal mesh size h is required");
@@ -252,6 +253,7 @@ __global__ void k_bc_values(int64_t nbc, const int32_t* __restrict__ bc_nodes, i
 void launch_bc_values(cfem_ctx* c, int kind, double value, double t, const double* user_vals, double* g) {
   if (c->nbc == 0) return;
   if (kind == CFEM_BC_USER && !user_vals) CFEM_THROW(-1, "CFEM_BC_USER needs bc_values");
+  ProfScope ps(c, PROF_MISC);
   k_bc_values<<<vec_grid(c, c->nbc), kBlock, 0, c->stream>>>(c->nbc, c->d_bc_nodes, kind, value, t, user_vals, c->dm.xy, g);
   LAUNCHED(c);
 }

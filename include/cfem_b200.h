@@ -171,6 +171,7 @@ typedef struct cfem_step_stats {
   int64_t kernel_launches;       /* every kernel of ours in the call    */
   double  last_newton_residual;
   double  time;                  /* simulation time after the call      */
+  double  device_ms;             /* CUDA-event time of the whole call on the context stream */
 } cfem_step_stats;
 
 /* Load / read the time-loop state (caller numbering, host or device).
@@ -197,6 +198,13 @@ int cfem_step_advection(cfem_ctx* ctx, const cfem_step_params* p, int n_steps, i
  * algorithmic bytes one launch moves. */
 enum { CFEM_KERNEL_SPMV = 0, CFEM_KERNEL_ASM_RESIDUAL = 1, CFEM_KERNEL_ASM_JACOBIAN = 2,
        CFEM_KERNEL_RV_EPSILON = 3, CFEM_KERNEL_ASM_RV_RHS = 4, CFEM_KERNEL_PCG_ITER = 5 };
+/* Bracket every kernel launch of the following calls with CUDA events (adds ~2 us
+ * per launch; use on a separate pass, not on the timed one).  cfem_profile_end sums
+ * the device time and launch count per category:
+ *   0 SpMV  1 vector assembly  2 matrix assembly  3 Krylov vector kernels
+ *   4 RV (stats + epsilon)     5 misc (gather/fill/axpy/bc)          (arrays of 8) */
+int cfem_profile_begin(cfem_ctx* ctx, int max_launches);
+int cfem_profile_end(cfem_ctx* ctx, double* ms_per_category, int64_t* launches_per_category);
 int cfem_time_kernel(cfem_ctx* ctx, int kernel, int flux, int reps, double* ms_per_launch,
                      double* algorithmic_bytes);
 
