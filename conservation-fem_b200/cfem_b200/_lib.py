@@ -19,13 +19,13 @@ FLUX_ADVECTION, FLUX_BURGERS, FLUX_KPP = 0, 1, 2
 BDF1, BDF2 = 1, 2
 EPS_NONLINEAR, EPS_LINEAR, EPS_POINTWISE, EPS_FIRST_ORDER, EPS_LINEAR_SIMPLE = 0, 1, 2, 3, 4
 MAT_MASS, MAT_MASS_BC, MAT_SYSTEM, MAT_STIFFNESS = 0, 1, 2, 3
-SOLVER_PCG, SOLVER_BICGSTAB, SOLVER_GMRES = 0, 1, 2
+SOLVER_PCG, SOLVER_BICGSTAB, SOLVER_GMRES, SOLVER_CHEBYSHEV = 0, 1, 2, 3
 BC_CONSTANT, BC_BURGERS_EXACT, BC_USER = 0, 1, 2
 ORDER_HILBERT, ORDER_NATURAL = 0, 1
 KERNEL_SPMV, KERNEL_ASM_RESIDUAL, KERNEL_ASM_JACOBIAN, KERNEL_RV_EPSILON, KERNEL_ASM_RV_RHS = 0, 1, 2, 3, 4
 
 FLUX_BY_NAME = {"advection": FLUX_ADVECTION, "burgers": FLUX_BURGERS, "kpp": FLUX_KPP}
-SOLVER_BY_NAME = {"pcg": SOLVER_PCG, "bicgstab": SOLVER_BICGSTAB, "gmres": SOLVER_GMRES}
+SOLVER_BY_NAME = {"pcg": SOLVER_PCG, "bicgstab": SOLVER_BICGSTAB, "gmres": SOLVER_GMRES, "chebyshev": SOLVER_CHEBYSHEV}
 
 
 class CfemError(RuntimeError):
@@ -41,7 +41,7 @@ class StepParams(C.Structure):
         ("newton_rtol", C.c_double), ("newton_atol", C.c_double),
         ("newton_max_it", C.c_int32), ("solver", C.c_int32),
         ("lin_rtol", C.c_double), ("lin_max_it", C.c_int32), ("bc_kind", C.c_int32),
-        ("bc_value", C.c_double), ("residual_bc", C.c_int32), ("reserved", C.c_int32),
+        ("bc_value", C.c_double), ("residual_bc", C.c_int32), ("mass_solver", C.c_int32),
     ]
 
 

@@ -248,7 +248,7 @@ def _flux(flux):
 
 def step_params(flux, dt, Cvel, Crv, scheme="bdf2", newton_rtol=1e-4, newton_atol=1e-10, newton_max_it=100,
                 solver="bicgstab", lin_rtol=1e-13, lin_max_it=2000, bc_kind="constant", bc_value=0.0,
-                residual_bc=True):
+                residual_bc=True, mass_solver="chebyshev"):
     p = L.StepParams()
     p.flux = _flux(flux)
     p.scheme = L.BDF2 if scheme in ("bdf2", 2) else L.BDF1
@@ -259,4 +259,5 @@ def step_params(flux, dt, Cvel, Crv, scheme="bdf2", newton_rtol=1e-4, newton_ato
     p.bc_kind = {"constant": L.BC_CONSTANT, "burgers_exact": L.BC_BURGERS_EXACT, "user": L.BC_USER}.get(bc_kind, bc_kind)
     p.bc_value = float(bc_value)
     p.residual_bc = int(bool(residual_bc))
+    p.mass_solver = 100 + L.SOLVER_PCG if mass_solver == "pcg" else 0
     return p

@@ -152,12 +152,20 @@ void build_user_csr(cfem_ctx* c) {
   }
 }
 
+// mass-matrix solves: Chebyshev unless the caller asks for PCG (mass_solver == 100 + CFEM_SOLVER_PCG)
+SolveResult mass_solve(cfem_ctx* c, int mass_solver, const Matrix& M, const double* b, double* x, double rtol,
+                       int max_it, int* predict) {
+  if (mass_solver == 100 + CFEM_SOLVER_PCG) return pcg(c, M, b, x, rtol, 0.0, max_it, predict);
+  return chebyshev_mass(c, M, b, x, rtol, max_it, predict);
+}
+
 SolveResult run_solver(cfem_ctx* c, int solver, const Matrix& A, const double* b, double* x, double rtol,
                        double atol, int max_it, int* predict) {
   switch (solver) {
     case CFEM_SOLVER_PCG: return pcg(c, A, b, x, rtol, atol, max_it, predict);
     case CFEM_SOLVER_BICGSTAB: return bicgstab(c, A, b, x, rtol, atol, max_it, predict);
     case CFEM_SOLVER_GMRES: return gmres(c, A, b, x, rtol, atol, max_it, predict);
+    case CFEM_SOLVER_CHEBYSHEV: return chebyshev_mass(c, A, b, x, rtol, max_it, predict);
     default: CFEM_THROW(-1, "unknown solver id");
   }
 }
@@ -314,8 +322,8 @@ int cfem_nodal_h(cfem_ctx* c, double* h_out, double rtol, int max_it, int* iters
   double* b = c->wk[8];
   launch_nodal_h_rhs(c, b);
   launch_fill(c, c->h, 0.0, c->dm.nn);
-  int predict = 24;
-  SolveResult r = pcg(c, c->mat[CFEM_MAT_MASS], b, c->h, rtol, 0.0, max_it, &predict);
+  int predict = 30;
+  SolveResult r = mass_solve(c, 0, c->mat[CFEM_MAT_MASS], b, c->h, rtol, max_it, &predict);
   if (iters) *iters = r.iters;
   if (h_out) export_vec(c, c->h, h_out);
   CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -338,7 +346,7 @@ int cfem_rv_residual(cfem_ctx* c, int flux, int scheme, double dt, const double*
   double* b = c->wk[8];
   launch_rv_rhs(c, flux, scheme, dt, c->u_n, c->u_old, u_oo ? c->u_oo : nullptr, w ? c->w : nullptr, use_bc != 0, b,
                 nullptr);
-  SolveResult r = pcg(c, c->mat[use_bc ? CFEM_MAT_MASS_BC : CFEM_MAT_MASS], b, c->RH, rtol, 0.0, max_it, &c->pcg_predict);
+  SolveResult r = mass_solve(c, 0, c->mat[use_bc ? CFEM_MAT_MASS_BC : CFEM_MAT_MASS], b, c->RH, rtol, max_it, &c->pcg_predict);
   if (iters) *iters = r.iters;
   export_vec(c, c->RH, R_io);
   CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -530,7 +538,7 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
     launch_bc_values(c, p->bc_kind, p->bc_value, c->t, d_bc_user ? d_bc_user + (int64_t)s * c->nbc : nullptr, c->g);
     // (a-3) residual projection  M_bc RH = b
     launch_rv_rhs(c, p->flux, p->scheme, p->dt, c->u_n, c->u_old, c->u_oo, nullptr, true, b, c->fluxn);
-    SolveResult rm = pcg(c, c->mat[CFEM_MAT_MASS_BC], b, c->RH, p->lin_rtol, 0.0, p->lin_max_it, &c->pcg_predict);
+    SolveResult rm = mass_solve(c, p->mass_solver, c->mat[CFEM_MAT_MASS_BC], b, c->RH, p->lin_rtol, p->lin_max_it, &c->pcg_predict);
     if (!rm.converged) CFEM_THROW(-3, "step_scalar: residual PCG did not converge");
     st.mass_iterations += rm.iters;
     // (a-4) nodal viscosity
@@ -600,8 +608,8 @@ int cfem_step_advection(cfem_ctx* c, const cfem_step_params* p, int n_steps, int
     if (!gfem) {
       // (a-3) BDF1 residual projection, RV_node.py:209-214
       launch_rv_rhs(c, CFEM_FLUX_ADVECTION, CFEM_BDF1, p->dt, c->u_n, c->u_old, nullptr, c->w, p->residual_bc != 0, b, nullptr);
-      SolveResult rm = pcg(c, c->mat[p->residual_bc ? CFEM_MAT_MASS_BC : CFEM_MAT_MASS], b, c->RH, p->lin_rtol, 0.0,
-                           p->lin_max_it, &c->pcg_predict);
+      SolveResult rm = mass_solve(c, p->mass_solver, c->mat[p->residual_bc ? CFEM_MAT_MASS_BC : CFEM_MAT_MASS], b, c->RH,
+                                  p->lin_rtol, p->lin_max_it, &c->pcg_predict);
       if (!rm.converged) CFEM_THROW(-3, "step_advection: residual PCG did not converge");
       st.mass_iterations += rm.iters;
       // (a-5) nodal viscosity

@@ -135,5 +135,5 @@ struct cfem_ctx {
   std::vector<int32_t> u_rowptr, u_colidx, u_slot;
   cfem::Launches launches;
   cfem::Profiler prof;
-  int pcg_predict = 8, krylov_predict = 8;
+  int pcg_predict = 28, krylov_predict = 8;
 };

@@ -36,6 +36,9 @@ void launch_sub(cfem_ctx* c, double* x, const double* dx, int64_t n);
 struct SolveResult { int iters; double relres; bool converged; };
 SolveResult pcg(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
                 int max_it, int* predict);
+// Chebyshev semi-iteration for the (Dirichlet-reduced) P1 mass matrix, spectrum of D^-1 M in [1/2, 2]
+SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, int max_it,
+                           int* predict);
 SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol,
                      double atol, int max_it, int* predict);
 SolveResult gmres(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol,

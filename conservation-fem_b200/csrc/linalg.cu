@@ -9,6 +9,9 @@
 // results are bitwise reproducible.  A device-side `done` flag turns the
 // remaining launches of a chunk into no-ops; the host polls it every few
 // iterations (after a predicted iteration count) instead of every iteration.
+#include <cstdlib>
+#include <string>
+
 #include "device_utils.cuh"
 #include "launch.h"
 
@@ -124,10 +127,78 @@ k_spmv(const int64_t nn, const int32_t* __restrict__ rowptr, const int32_t* __re
   }
 }
 
+// CSR-stream SpMV: a CTA takes one assembly tile (<= kTileNodes consecutive rows,
+// <= kTileNnzCap entries).  Every thread streams entries p, p+256, ... of the
+// tile's contiguous CSR segment (vals/colidx fully coalesced, loads independent
+// -> deep memory-level parallelism), multiplies by the gathered x[col] and parks
+// the product in shared memory; then thread r sums row r's products in column
+// order.  Fixed order, no atomics.
+template <int NDOT>
+__global__ void __launch_bounds__(kTileNodes)
+k_spmv_stream(const int ntiles, const int32_t* __restrict__ tile_node, const int32_t* __restrict__ rowptr,
+              const int32_t* __restrict__ colidx, const double* __restrict__ vals, const double* __restrict__ x,
+              double* __restrict__ y, const double* __restrict__ d0, const double* __restrict__ d1,
+              double* __restrict__ part0, double* __restrict__ part1, const int32_t* __restrict__ status) {
+  if (status && status[0]) return;
+  __shared__ double prod[kTileNnzCap];
+  __shared__ int32_t rp[kTileNodes + 1];
+  __shared__ double red[9];
+  const int tid = threadIdx.x;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
+    for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i];
+    __syncthreads();
+    const int start = rp[0], cnt = rp[nrows] - start;
+    const double* __restrict__ v = vals + start;
+    const int32_t* __restrict__ ci = colidx + start;
+    int p = tid;
+    for (; p + 3 * kTileNodes < cnt; p += 4 * kTileNodes) {
+      const int c0 = ci[p], c1 = ci[p + kTileNodes], c2 = ci[p + 2 * kTileNodes], c3 = ci[p + 3 * kTileNodes];
+      const double v0 = v[p], v1 = v[p + kTileNodes], v2 = v[p + 2 * kTileNodes], v3 = v[p + 3 * kTileNodes];
+      const double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+      prod[p] = v0 * x0;
+      prod[p + kTileNodes] = v1 * x1;
+      prod[p + 2 * kTileNodes] = v2 * x2;
+      prod[p + 3 * kTileNodes] = v3 * x3;
+    }
+    for (; p < cnt; p += kTileNodes) prod[p] = v[p] * x[ci[p]];
+    __syncthreads();
+    if (tid < nrows) {
+      const int a = rp[tid] - start, b = rp[tid + 1] - start;
+      double s = 0.0;
+      for (int k = a; k < b; ++k) s += prod[k];
+      const int row = n0 + tid;
+      y[row] = s;
+      if (NDOT >= 1) acc0 += s * (d0 == y ? s : d0[row]);
+      if (NDOT >= 2) acc1 += s * (d1 == y ? s : d1[row]);
+    }
+    __syncthreads();
+  }
+  if (NDOT >= 1) {
+    acc0 = block_sum(acc0, red);
+    if (tid == 0) part0[blockIdx.x] = acc0;
+  }
+  if (NDOT >= 2) {
+    acc1 = block_sum(acc1, red);
+    if (tid == 0) part1[blockIdx.x] = acc1;
+  }
+}
+
+static int g_spmv_mode = -1;  // 0 = stream (default), 1 = sub-warp per row (CFEM_SPMV=subwarp)
+static inline int spmv_mode() {
+  if (g_spmv_mode < 0) {
+    const char* e = getenv("CFEM_SPMV");
+    g_spmv_mode = (e && std::string(e) == "subwarp") ? 1 : 0;
+  }
+  return g_spmv_mode;
+}
+
 static inline int spmv_grid(const cfem_ctx* c) {
+  const int64_t cap = (int64_t)c->sm_count * 8;
+  if (spmv_mode() == 0) return (int)(c->dm.ntiles < cap ? c->dm.ntiles : cap);
   const int64_t rows_per_block = (kBlock / 32) * 4;
   int64_t b = (c->dm.nn + rows_per_block - 1) / rows_per_block;
-  const int64_t cap = (int64_t)c->sm_count * 8;
   return (int)(b < cap ? b : cap);
 }
 
@@ -135,14 +206,144 @@ template <int NDOT>
 static void spmv_dots(cfem_ctx* c, const Matrix& A, const double* x, double* y, const double* d0,
                       const double* d1, double* p0, double* p1, bool gated) {
   ProfScope ps(c, PROF_SPMV);
-  k_spmv<8, NDOT><<<spmv_grid(c), kBlock, 0, c->stream>>>(c->dm.nn, c->dm.rowptr, c->dm.colidx, A.vals, x, y, d0,
-                                                          d1, p0, p1, gated ? c->status : nullptr);
+  if (spmv_mode() == 0)
+    k_spmv_stream<NDOT><<<spmv_grid(c), kTileNodes, 0, c->stream>>>(c->dm.ntiles, c->dm.tile_node, c->dm.rowptr,
+                                                                    c->dm.colidx, A.vals, x, y, d0, d1, p0, p1,
+                                                                    gated ? c->status : nullptr);
+  else
+    k_spmv<8, NDOT><<<spmv_grid(c), kBlock, 0, c->stream>>>(c->dm.nn, c->dm.rowptr, c->dm.colidx, A.vals, x, y, d0,
+                                                            d1, p0, p1, gated ? c->status : nullptr);
   LAUNCHED(c);
   c->launches.spmv++;
 }
 
 void launch_spmv(cfem_ctx* c, const Matrix& A, const double* x, double* y) {
   spmv_dots<0>(c, A, x, y, nullptr, nullptr, nullptr, nullptr, false);
+}
+
+// ---------------------------------------------------------------- Chebyshev (mass matrix)
+// For P1 triangles every eigenvalue of D^-1 M lies in [1/2, 2] (element-wise bound,
+// inherited by the Dirichlet-reduced matrix), so the Chebyshev semi-iteration needs
+// no inner products: one fused kernel per iteration (SpMV + residual + update), no
+// reductions, no host round trips until the final check.
+//   r_k = b - M x_k ; z_k = D^-1 r_k ; d_k = c1 d_{k-1} + c2 z_k ; x_{k+1} = x_k + d_k
+template <bool FIRST>
+__global__ void __launch_bounds__(kTileNodes)
+k_cheb_stream(const int ntiles, const int32_t* __restrict__ tile_node, const int32_t* __restrict__ rowptr,
+              const int32_t* __restrict__ colidx, const double* __restrict__ vals, const double* __restrict__ dinv,
+              const double* __restrict__ b, const double* __restrict__ xk, double* __restrict__ xn,
+              double* __restrict__ d, const double c1, const double c2, double* __restrict__ part_rr,
+              double* __restrict__ part_bb) {
+  __shared__ double prod[kTileNnzCap];
+  __shared__ int32_t rp[kTileNodes + 1];
+  __shared__ double red[9];
+  const int tid = threadIdx.x;
+  double rr = 0.0, bb = 0.0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
+    for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i];
+    __syncthreads();
+    const int start = rp[0], cnt = rp[nrows] - start;
+    const double* __restrict__ v = vals + start;
+    const int32_t* __restrict__ ci = colidx + start;
+    int p = tid;
+    for (; p + 3 * kTileNodes < cnt; p += 4 * kTileNodes) {
+      const int c0 = ci[p], c1i = ci[p + kTileNodes], c2i = ci[p + 2 * kTileNodes], c3 = ci[p + 3 * kTileNodes];
+      const double v0 = v[p], v1 = v[p + kTileNodes], v2 = v[p + 2 * kTileNodes], v3 = v[p + 3 * kTileNodes];
+      const double x0 = xk[c0], x1 = xk[c1i], x2 = xk[c2i], x3 = xk[c3];
+      prod[p] = v0 * x0;
+      prod[p + kTileNodes] = v1 * x1;
+      prod[p + 2 * kTileNodes] = v2 * x2;
+      prod[p + 3 * kTileNodes] = v3 * x3;
+    }
+    for (; p < cnt; p += kTileNodes) prod[p] = v[p] * xk[ci[p]];
+    __syncthreads();
+    if (tid < nrows) {
+      const int a = rp[tid] - start, e = rp[tid + 1] - start;
+      double s = 0.0;
+      for (int k = a; k < e; ++k) s += prod[k];
+      const int row = n0 + tid;
+      const double bi = b[row], r = bi - s, z = dinv[row] * r;
+      const double dk = FIRST ? c2 * z : c1 * d[row] + c2 * z;
+      d[row] = dk;
+      xn[row] = xk[row] + dk;
+      rr += r * r;
+      if (FIRST) bb += bi * bi;
+    }
+    __syncthreads();
+  }
+  rr = block_sum(rr, red);
+  if (tid == 0) part_rr[blockIdx.x] = rr;
+  if (FIRST) {
+    bb = block_sum(bb, red);
+    if (tid == 0) part_bb[blockIdx.x] = bb;
+  }
+}
+
+// writes sqrt(rr/bb) to scalars[S_RELRES] from the partials
+__global__ void __launch_bounds__(kBlock)
+k_relres(const double* __restrict__ part, int npart, double* __restrict__ scalars) {
+  __shared__ double red[9];
+  const double rr = reduce_partials(part + P_RR * kMaxPartials, npart, red);
+  const double bb = reduce_partials(part + P_BB * kMaxPartials, npart, red);
+  if (threadIdx.x == 0) { scalars[S_RR] = rr; scalars[S_BB] = bb; scalars[S_RELRES] = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr); }
+}
+
+SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, int max_it,
+                           int* predict) {
+  const int64_t n = c->dm.nn;
+  double *xa = x, *xb = c->wk[0], *d = c->wk[1];
+  double* part = c->partials;
+  const int gs = spmv_grid(c);
+  const double lmin = 0.5, lmax = 2.0;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
+  double rho = 1.0 / sigma1;
+  SolveResult res{0, 0.0, false};
+  int it = 0;
+  int target = predict ? *predict : 28;
+  if (target < 2) target = 2;
+  if (target > max_it) target = max_it;
+  while (true) {
+    for (; it < target; ++it) {
+      ProfScope ps(c, PROF_SPMV);
+      if (it == 0) {
+        k_cheb_stream<true><<<gs, kTileNodes, 0, c->stream>>>(c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
+                                                             A.vals, A.dinv, b, xa, xb, d, 0.0, 1.0 / theta,
+                                                             part + P_RR * kMaxPartials, part + P_BB * kMaxPartials);
+      } else {
+        const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+        k_cheb_stream<false><<<gs, kTileNodes, 0, c->stream>>>(c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
+                                                              A.vals, A.dinv, b, xa, xb, d, rho_new * rho,
+                                                              2.0 * rho_new / delta, part + P_RR * kMaxPartials, nullptr);
+        rho = rho_new;
+      }
+      LAUNCHED(c);
+      c->launches.spmv++;
+      std::swap(xa, xb);
+    }
+    // the last kernel measured ||b - M x_{it-1}||; x_it is one update further on
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_relres<<<1, kBlock, 0, c->stream>>>(part, gs, c->scalars); LAUNCHED(c); }
+    CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + S_RELRES, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    res.iters = it;
+    res.relres = c->h_pinned[0];
+    if (!(res.relres == res.relres)) break;
+    if (res.relres <= rtol) { res.converged = true; break; }
+    if (it >= max_it) break;
+    // error contracts by ~1/3 per iteration: extend by what the bound asks for, at least 2
+    int more = (int)ceil(log(res.relres / rtol) / log(3.0));
+    if (more < 2) more = 2;
+    target = it + more;
+    if (target > max_it) target = max_it;
+  }
+  if (xa != x) launch_copy(c, x, xa, n);
+  if (predict) {
+    // next solve: drop the iterations the achieved residual shows were not needed (keep one spare)
+    int spare = (res.converged && res.relres > 0.0) ? (int)floor(log(rtol / res.relres) / log(3.0)) - 1 : 0;
+    if (spare < 0) spare = 0;
+    *predict = res.iters - spare > 2 ? res.iters - spare : 2;
+  }
+  return res;
 }
 
 // ---------------------------------------------------------------- PCG

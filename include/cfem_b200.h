@@ -42,7 +42,8 @@ enum { CFEM_MAT_MASS = 0,          /* int u v, no Dirichlet rows              */
        CFEM_MAT_MASS_BC = 1,       /* same, Dirichlet rows/cols -> identity   */
        CFEM_MAT_SYSTEM = 2,        /* last assembled CN matrix / Jacobian     */
        CFEM_MAT_STIFFNESS = 3      /* last assembled int eps grad u . grad v  */ };
-enum { CFEM_SOLVER_PCG = 0, CFEM_SOLVER_BICGSTAB = 1, CFEM_SOLVER_GMRES = 2 };
+enum { CFEM_SOLVER_PCG = 0, CFEM_SOLVER_BICGSTAB = 1, CFEM_SOLVER_GMRES = 2,
+       CFEM_SOLVER_CHEBYSHEV = 3 /* mass matrices only: spectrum of D^-1 M in [1/2,2] */ };
 enum { CFEM_BC_CONSTANT = 0,       /* g = bc_value             KPP_exact.py:88 */
        CFEM_BC_BURGERS_EXACT = 1,  /* g = exact Riemann soln   Exact_Burger_RV.py:37-66,172-176 */
        CFEM_BC_USER = 2            /* g given per call, one value per Dirichlet dof */ };
@@ -158,7 +159,7 @@ typedef struct cfem_step_params {
   int32_t bc_kind;       /* CFEM_BC_*                                            */
   double bc_value;       /* CFEM_BC_CONSTANT                                     */
   int32_t residual_bc;   /* advection: project the residual with bc (RV_node.py:213) or without (RV_node_convergence.py:188) */
-  int32_t reserved;
+  int32_t mass_solver;   /* CFEM_SOLVER_CHEBYSHEV (default, 0 maps to it) or CFEM_SOLVER_PCG+100 */
 } cfem_step_params;
 
 typedef struct cfem_step_stats {

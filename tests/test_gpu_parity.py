@@ -177,14 +177,14 @@ def test_advection_system(case):
         assert abs(Ag - Ar).max() <= 1e-13 * abs(Ar).max()
 
 
-@pytest.mark.parametrize("solver", ["pcg", "bicgstab"])
+@pytest.mark.parametrize("solver", ["pcg", "chebyshev", "bicgstab"])
 def test_krylov_vs_lu(case, solver):
     from scipy.sparse.linalg import splu
 
     _, x, c, ctx, m = case
     uh, u_n, _, _, rng = fields(m)
     b = rng.normal(size=m.n)
-    if solver == "pcg":
+    if solver in ("pcg", "chebyshev"):
         which, A = L.MAT_MASS, m.M
     else:
         eps = rng.uniform(0.0, 0.05, size=m.n)
