@@ -225,7 +225,7 @@ class Context:
         L.check(self._lib.cfem_time_kernel(self._h, int(kernel), _flux(flux), int(reps), C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
-    PROFILE_CATEGORIES = ("spmv", "asm_vector", "asm_matrix", "krylov_vector", "rv", "misc")
+    PROFILE_CATEGORIES = ("spmv", "asm_vector", "asm_matrix", "krylov_vector", "rv", "misc", "chebyshev")
 
     def profile_begin(self, max_launches=200000):
         L.check(self._lib.cfem_profile_begin(self._h, int(max_launches)))

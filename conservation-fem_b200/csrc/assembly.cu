@@ -429,20 +429,29 @@ int assembly_grid(const cfem_ctx* c) {
   return c->dm.ntiles < want ? c->dm.ntiles : want;
 }
 
+// Launches one persistent CTA per resident slot (occupancy x SM count), each looping
+// over tiles; returns the grid size (== number of per-CTA partials written).
 template <class Op>
-static void run_tiles(cfem_ctx* c, const Op& op, bool bc, double* vals, double* dinv, double* partials) {
+static int run_tiles(cfem_ctx* c, const Op& op, bool bc, double* vals, double* dinv, double* partials) {
   const int ccap = c->hm.max_tile_cells, nnzcap = c->hm.max_tile_nnz;
   const size_t smem = sizeof(double) * ((size_t)Op::NV * 3 * ccap + (Op::MAT ? (size_t)9 * ccap + nnzcap : 0));
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
+  static int occ = 0;  // per template instantiation (one mesh capacity per process is the common case)
+  static size_t occ_smem = 0;
+  if (occ == 0 || occ_smem != smem) {
     CUDA_OK(cudaFuncSetAttribute(k_tile_assemble<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile_assemble<Op>, kTileNodes, smem));
+    if (occ < 1) CFEM_THROW(-2, "assembly kernel does not fit on an SM");
+    occ_smem = smem;
   }
+  int grid = c->sm_count * occ;
+  if (grid > c->dm.ntiles) grid = c->dm.ntiles;
+  if (grid > kMaxPartials) grid = kMaxPartials;
   ProfScope ps(c, Op::MAT ? PROF_ASM_MAT : PROF_ASM_VEC);
-  k_tile_assemble<Op><<<assembly_grid(c), kTileNodes, smem, c->stream>>>(c->dm, op, bc, vals, dinv, partials, ccap, nnzcap);
+  k_tile_assemble<Op><<<grid, kTileNodes, smem, c->stream>>>(c->dm, op, bc, vals, dinv, partials, ccap, nnzcap);
   CUDA_OK(cudaGetLastError());
   c->launches.total++;
   c->launches.assembly++;
+  return grid;
 }
 
 void launch_mass(cfem_ctx* c, Matrix& M, bool bc) {
@@ -489,10 +498,8 @@ template <int FLUX>
 static int cn_residual_t(cfem_ctx* c, double dt, const double* uh, const double* u_n, const double* eps,
                          const double* g, const double* fluxn, double* F, double* partials) {
   if (fluxn)
-    run_tiles(c, CnResidualOp<FLUX, true>{uh, u_n, eps, g, fluxn, c->dm.is_bc, 0.5 * dt, F}, true, nullptr, nullptr, partials);
-  else
-    run_tiles(c, CnResidualOp<FLUX, false>{uh, u_n, eps, g, fluxn, c->dm.is_bc, 0.5 * dt, F}, true, nullptr, nullptr, partials);
-  return assembly_grid(c);
+    return run_tiles(c, CnResidualOp<FLUX, true>{uh, u_n, eps, g, fluxn, c->dm.is_bc, 0.5 * dt, F}, true, nullptr, nullptr, partials);
+  return run_tiles(c, CnResidualOp<FLUX, false>{uh, u_n, eps, g, fluxn, c->dm.is_bc, 0.5 * dt, F}, true, nullptr, nullptr, partials);
 }
 
 int launch_cn_residual(cfem_ctx* c, int flux, double dt, const double* uh, const double* u_n,

@@ -83,7 +83,7 @@ struct Launches {  // counters of our own kernel launches
 };
 
 // Optional per-launch CUDA-event bracketing (bench.py roofline leg).
-enum { PROF_SPMV = 0, PROF_ASM_VEC = 1, PROF_ASM_MAT = 2, PROF_KRYLOV_VEC = 3, PROF_RV = 4, PROF_MISC = 5, PROF_NCAT = 8 };
+enum { PROF_SPMV = 0, PROF_ASM_VEC = 1, PROF_ASM_MAT = 2, PROF_KRYLOV_VEC = 3, PROF_RV = 4, PROF_MISC = 5, PROF_CHEB = 6, PROF_NCAT = 8 };
 struct Profiler {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs

@@ -305,7 +305,7 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
   if (target > max_it) target = max_it;
   while (true) {
     for (; it < target; ++it) {
-      ProfScope ps(c, PROF_SPMV);
+      ProfScope ps(c, PROF_CHEB);
       if (it == 0) {
         k_cheb_stream<true><<<gs, kTileNodes, 0, c->stream>>>(c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
                                                              A.vals, A.dinv, b, xa, xb, d, 0.0, 1.0 / theta,

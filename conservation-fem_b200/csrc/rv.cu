@@ -111,6 +111,59 @@ k_epsilon_patch(const int64_t nn, const int32_t* __restrict__ rowptr, const int3
   }
 }
 
+// Tile-streamed form of the same computation: the tile's column indices are staged in
+// shared memory once (coalesced), then three coalesced gather passes (u_n, |Rh|, beta)
+// park values in shared memory and thread r reduces row r's patch.
+template <bool LINEAR>
+__global__ void __launch_bounds__(kTileNodes)
+k_epsilon_stream(const int ntiles, const int64_t nn, const int32_t* __restrict__ tile_node,
+                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                 const double* __restrict__ u_n, const double* __restrict__ Rh, const double* __restrict__ beta,
+                 const double2* __restrict__ w, const double* __restrict__ h, const double* __restrict__ part,
+                 int npart, double Cvel, double Crv, double* __restrict__ eps) {
+  __shared__ double val[kTileNnzCap];
+  __shared__ int32_t col[kTileNnzCap];
+  __shared__ int32_t rp[kTileNodes + 1];
+  __shared__ double red[9];
+  const double A = absolute_term(part, npart, nn, red);
+  const int tid = threadIdx.x;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
+    for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i];
+    __syncthreads();
+    const int start = rp[0], cnt = rp[nrows] - start;
+    for (int p = tid; p < cnt; p += kTileNodes) { const int j = colidx[start + p]; col[p] = j; val[p] = u_n[j]; }
+    __syncthreads();
+    const int a = tid < nrows ? rp[tid] - start : 0, e = tid < nrows ? rp[tid + 1] - start : 0;
+    double umax = -INFINITY, umin = INFINITY, rmax = 0.0, bmax = 0.0;
+    for (int k = a; k < e; ++k) { umax = fmax(umax, val[k]); umin = fmin(umin, val[k]); }
+    __syncthreads();
+    for (int p = tid; p < cnt; p += kTileNodes) val[p] = fabs(Rh[col[p]]);
+    __syncthreads();
+    for (int k = a; k < e; ++k) rmax = fmax(rmax, val[k]);
+    if (!LINEAR) {
+      __syncthreads();
+      for (int p = tid; p < cnt; p += kTileNodes) val[p] = beta[col[p]];
+      __syncthreads();
+      for (int k = a; k < e; ++k) bmax = fmax(bmax, val[k]);
+    }
+    if (tid < nrows) {
+      const int row = n0 + tid;
+      if (LINEAR) {
+        const double2 wi = w[row];  // centre node, RV.py:113-115
+        bmax = sqrt(__dadd_rn(__dmul_rn(wi.x, wi.x), __dmul_rn(wi.y, wi.y)));
+      }
+      const double hi = h[row];
+      const double n_i = fabs((umax - umin) - A);
+      const double Ri = rmax / n_i;
+      const double first = __dmul_rn(__dmul_rn(Cvel, hi), bmax);
+      const double second = __dmul_rn(__dmul_rn(Crv, __dmul_rn(hi, hi)), fabs(Ri));
+      eps[row] = pymin(first, second);
+    }
+    __syncthreads();
+  }
+}
+
 // pointwise variants: RV.get_epsilon (RV.py:27-40), get_epsilon_1storder (RV.py:42-54),
 // get_epsilon_linear_simple (RV.py:129-142; also normalises Rh in place)
 template <int FLUX>
@@ -164,16 +217,14 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
       CFEM_THROW(-1, "rv_epsilon(nonlinear): flux must be BURGERS or KPP");
     }
     LAUNCHED(c);
-    const int64_t rows_per_block = (kBlock / 32) * 4;
-    int64_t g = (n + rows_per_block - 1) / rows_per_block;
-    const int64_t cap = (int64_t)c->sm_count * 8;
-    if (g > cap) g = cap;
+    int64_t g = (int64_t)c->sm_count * 4;
+    if (g > c->dm.ntiles) g = c->dm.ntiles;
     if (variant == CFEM_EPS_LINEAR)
-      k_epsilon_patch<8, true><<<(int)g, kBlock, 0, c->stream>>>(n, c->dm.rowptr, c->dm.colidx, u_n, Rh, nullptr, w, h,
-                                                               c->partials, gv, Cvel, Crv, eps);
+      k_epsilon_stream<true><<<(int)g, kTileNodes, 0, c->stream>>>(c->dm.ntiles, n, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
+                                                                 u_n, Rh, nullptr, w, h, c->partials, gv, Cvel, Crv, eps);
     else
-      k_epsilon_patch<8, false><<<(int)g, kBlock, 0, c->stream>>>(n, c->dm.rowptr, c->dm.colidx, u_n, Rh, beta, w, h,
-                                                                c->partials, gv, Cvel, Crv, eps);
+      k_epsilon_stream<false><<<(int)g, kTileNodes, 0, c->stream>>>(c->dm.ntiles, n, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
+                                                                  u_n, Rh, beta, w, h, c->partials, gv, Cvel, Crv, eps);
     LAUNCHED(c);
     return;
   }

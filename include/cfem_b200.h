@@ -203,7 +203,8 @@ enum { CFEM_KERNEL_SPMV = 0, CFEM_KERNEL_ASM_RESIDUAL = 1, CFEM_KERNEL_ASM_JACOB
  * per launch; use on a separate pass, not on the timed one).  cfem_profile_end sums
  * the device time and launch count per category:
  *   0 SpMV  1 vector assembly  2 matrix assembly  3 Krylov vector kernels
- *   4 RV (stats + epsilon)     5 misc (gather/fill/axpy/bc)          (arrays of 8) */
+ *   4 RV (stats + epsilon)     5 misc (gather/fill/axpy/bc)
+ *   6 fused Chebyshev mass-solve iteration (SpMV + update)              (arrays of 8) */
 int cfem_profile_begin(cfem_ctx* ctx, int max_launches);
 int cfem_profile_end(cfem_ctx* ctx, double* ms_per_category, int64_t* launches_per_category);
 int cfem_time_kernel(cfem_ctx* ctx, int kernel, int flux, int reps, double* ms_per_launch,
