@@ -66,6 +66,7 @@ _L = C.c_int64
 SIGNATURES = {
     "cfem_last_error": (C.c_char_p, []),
     "cfem_version": (_I, []),
+    "cfem_struct_size": (_I, [_I]),
     "cfem_device_count": (_I, []),
     "cfem_create": (_I, [C.POINTER(_P), _I, _L, _L, _P, _I, _P, _I, _I]),
     "cfem_destroy": (None, [_P]),

@@ -177,6 +177,7 @@ extern "C" {
 
 const char* cfem_last_error(void) { return g_error.c_str(); }
 int cfem_version(void) { return 100; }
+int cfem_struct_size(int which) { return which == 0 ? (int)sizeof(cfem_step_params) : (which == 1 ? (int)sizeof(cfem_step_stats) : -1); }
 int cfem_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -51,6 +51,8 @@ enum { CFEM_ORDER_HILBERT = 0, CFEM_ORDER_NATURAL = 1 };
 
 const char* cfem_last_error(void);
 int cfem_version(void);
+/* sizeof(cfem_step_params) (which = 0) / sizeof(cfem_step_stats) (which = 1): lets a binding check its struct layout */
+int cfem_struct_size(int which);
 /* number of CUDA devices visible (0 if none / no driver) */
 int cfem_device_count(void);
 
