@@ -476,6 +476,9 @@ int cfem_state_set(cfem_ctx* c, const double* uh, const double* u_n, const doubl
   if (h) import_vec(c, h, c->h);
   if (w) import_vec2(c, w, c->w);
   c->t = t;
+  // iteration-count predictions restart with the state, so a run is a pure function of its inputs
+  c->pcg_predict = 28;
+  c->krylov_predict = 8;
   CUDA_OK(cudaStreamSynchronize(c->stream));
   API_END
 }
