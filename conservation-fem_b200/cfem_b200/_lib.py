@@ -69,6 +69,11 @@ SIGNATURES = {
     "cfem_struct_size": (_I, [_I]),
     "cfem_device_count": (_I, []),
     "cfem_create": (_I, [C.POINTER(_P), _I, _L, _L, _P, _I, _P, _I, _I]),
+    "cfem_nccl_unique_id": (_I, [_P]),
+    "cfem_create_distributed": (_I, [C.POINTER(_P), _I, _I, _I, _P, _L, _L, _P, _I, _P, _I, _I]),
+    "cfem_num_owned": (_L, [_P]),
+    "cfem_num_ghosts": (_L, [_P]),
+    "cfem_comm_stats": (_I, [_P, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L)]),
     "cfem_destroy": (None, [_P]),
     "cfem_synchronize": (_I, [_P]),
     "cfem_num_nodes": (_L, [_P]),
@@ -100,17 +105,22 @@ SIGNATURES = {
     "cfem_profile_end": (_I, [_P, C.POINTER(_D), C.POINTER(_L)]),
     "cfem_time_kernel": (_I, [_P, _I, _I, _I, C.POINTER(_D), C.POINTER(_D)]),
     "cfem_host_analyse": (_I, [C.POINTER(_P), _L, _L, _P, _I, _P, _I, _I]),
+    "cfem_host_analyse_part": (_I, [C.POINTER(_P), _I, _I, _L, _L, _P, _I, _P, _I, _I]),
+    "cfem_host_info": (_L, [_P, _I]),
     "cfem_host_size": (_L, [_P, _I]),
     "cfem_host_copy": (_I, [_P, _I, _P]),
     "cfem_host_free": (None, [_P]),
 }
 
 HM_ARRAYS = {"n2u": 0, "cells": 1, "rowptr": 2, "colidx": 3, "v2c_ptr": 4, "v2c_code": 5, "tile_node": 6,
-             "tile_cellptr": 7, "tile_cells": 8, "is_bnd": 9, "bnd_user": 10}
+             "tile_cellptr": 7, "tile_cells": 8, "is_bnd": 9, "bnd_user": 10, "peer_rank": 11, "send_ptr": 12,
+             "send_idx": 13, "recv_off": 14, "recv_cnt": 15}
 
 
-def host_analyse(x, cells, order=ORDER_HILBERT):
-    """Run the once-per-mesh host analysis (no GPU needed) and return its arrays."""
+def host_analyse(x, cells, order=ORDER_HILBERT, rank=0, world=1):
+    """Run the once-per-mesh host analysis (no GPU needed) and return its arrays.
+
+    With ``world > 1``: rank's part of the partition (local numbering: owned nodes, then ghosts)."""
     lib = load()
     x = np.ascontiguousarray(x, dtype=np.float64)
     cells = np.ascontiguousarray(cells)
@@ -118,7 +128,8 @@ def host_analyse(x, cells, order=ORDER_HILBERT):
     if ib == 4:
         cells = np.ascontiguousarray(cells, dtype=np.int32)
     h = C.c_void_p()
-    check(lib.cfem_host_analyse(C.byref(h), x.shape[0], cells.shape[0], ptr(x), x.shape[1], ptr(cells), ib, order))
+    check(lib.cfem_host_analyse_part(C.byref(h), rank, world, x.shape[0], cells.shape[0], ptr(x), x.shape[1],
+                                     ptr(cells), ib, order))
     out = {}
     try:
         for name, what in HM_ARRAYS.items():
@@ -127,6 +138,8 @@ def host_analyse(x, cells, order=ORDER_HILBERT):
             a = np.empty(n, dtype=dt)
             check(lib.cfem_host_copy(h, what, ptr(a)))
             out[name] = a
+        for k, name in enumerate(("n_owned", "n_local", "n_global", "n_cells", "nnz")):
+            out[name] = int(lib.cfem_host_info(h, k))
     finally:
         lib.cfem_host_free(h)
     return out

@@ -35,17 +35,30 @@ class Context:
 
     _cache: "weakref.WeakValueDictionary" = weakref.WeakValueDictionary()
 
-    def __init__(self, domain, device=0, order="hilbert"):
+    def __init__(self, domain, device=0, order="hilbert", comm=None):
+        """``comm``: None (one GPU) or ``(rank, world, nccl_id_bytes)`` from ``distributed.make_comm``.
+        In a distributed context every rank passes the same global mesh and global-sized fields;
+        results come back at the dofs the rank owns (``distributed.allgather_field`` merges them)."""
         lib = L.load()
         x, cells = as_mesh(domain)
         self.x = x
         self.cells = cells
         self.n = x.shape[0]
         h = C.c_void_p()
-        L.check(lib.cfem_create(C.byref(h), int(device), x.shape[0], cells.shape[0], L.ptr(x), 2,
-                                L.ptr(cells), 4, L.ORDER_HILBERT if order == "hilbert" else L.ORDER_NATURAL))
+        o = L.ORDER_HILBERT if order == "hilbert" else L.ORDER_NATURAL
+        self.rank, self.world = 0, 1
+        if comm is None or comm[1] == 1:
+            L.check(lib.cfem_create(C.byref(h), int(device), x.shape[0], cells.shape[0], L.ptr(x), 2,
+                                    L.ptr(cells), 4, o))
+        else:
+            self.rank, self.world, nid = int(comm[0]), int(comm[1]), comm[2]
+            buf = (C.c_char * 128).from_buffer_copy(bytes(nid))
+            L.check(lib.cfem_create_distributed(C.byref(h), int(device), self.rank, self.world, C.addressof(buf),
+                                                x.shape[0], cells.shape[0], L.ptr(x), 2, L.ptr(cells), 4, o))
         self._h = h
         self._lib = lib
+        self.n_owned = lib.cfem_num_owned(h)
+        self.n_ghosts = lib.cfem_num_ghosts(h)
         self.nnz = lib.cfem_num_nonzeros(h)
         self._pattern = None
         self._h_nodal = None
@@ -225,7 +238,7 @@ class Context:
         L.check(self._lib.cfem_time_kernel(self._h, int(kernel), _flux(flux), int(reps), C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
-    PROFILE_CATEGORIES = ("spmv", "asm_vector", "asm_matrix", "krylov_vector", "rv", "misc", "chebyshev")
+    PROFILE_CATEGORIES = ("spmv", "asm_vector", "asm_matrix", "krylov_vector", "rv", "misc", "chebyshev", "comm")
 
     def profile_begin(self, max_launches=200000):
         L.check(self._lib.cfem_profile_begin(self._h, int(max_launches)))
@@ -235,6 +248,15 @@ class Context:
         cnt = (C.c_int64 * 8)()
         L.check(self._lib.cfem_profile_end(self._h, ms, cnt))
         return {k: {"ms": ms[i], "launches": cnt[i]} for i, k in enumerate(self.PROFILE_CATEGORIES)}
+
+    def owned_dofs(self):
+        """Caller-numbered dofs this rank owns (all of them on one GPU)."""
+        return self.ordering()[: self.n_owned]
+
+    def comm_stats(self):
+        a, b, d = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        L.check(self._lib.cfem_comm_stats(self._h, C.byref(a), C.byref(b), C.byref(d)))
+        return {"halo_exchanges": a.value, "allreduces": b.value, "halo_doubles_sent_per_exchange": d.value}
 
     def synchronize(self):
         L.check(self._lib.cfem_synchronize(self._h))

@@ -61,28 +61,54 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-// caller array (host or device, caller numbering) -> internal-order device vector
+// caller array (host or device, caller numbering, GLOBAL size) -> local-order device vector
+// (owned + ghost entries, so imported fields arrive with valid ghosts)
 void import_vec(cfem_ctx* c, const double* user, double* dst, int stage_slot = 0) {
   const int64_t n = c->dm.nn;
-  const double* src = user;
-  if (!is_device_ptr(user)) {
-    CUDA_OK(cudaMemcpyAsync(c->stage[stage_slot], user, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    src = c->stage[stage_slot];
+  if (is_device_ptr(user)) { launch_gather(c, user, c->d_n2u, dst, n); return; }
+  if (c->world > 1) {
+    // distributed: gather this rank's entries on the host, ship only those
+    CUDA_OK(cudaStreamSynchronize(c->stream));  // h_stage may still feed an earlier copy
+    const int32_t* n2u = c->hm.n2u.data();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) c->h_stage[i] = user[n2u[i]];
+    CUDA_OK(cudaMemcpyAsync(dst, c->h_stage, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return;
   }
-  launch_gather(c, src, c->d_n2u, dst, n);
+  CUDA_OK(cudaMemcpyAsync(c->stage[stage_slot], user, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_gather(c, c->stage[stage_slot], c->d_n2u, dst, n);
 }
 void import_vec2(cfem_ctx* c, const double* user, double2* dst) {
   const int64_t n = c->dm.nn;
-  const double2* src = (const double2*)user;
-  if (!is_device_ptr(user)) {
-    // stage[2] and stage[3] are contiguous (allocated as one block)
-    CUDA_OK(cudaMemcpyAsync(c->stage[2], user, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    src = (const double2*)c->stage[2];
+  if (is_device_ptr(user)) { launch_gather2(c, (const double2*)user, c->d_n2u, dst, n); return; }
+  if (c->world > 1) {
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    const int32_t* n2u = c->hm.n2u.data();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      c->h_stage[2 * i] = user[2 * (int64_t)n2u[i]];
+      c->h_stage[2 * i + 1] = user[2 * (int64_t)n2u[i] + 1];
+    }
+    CUDA_OK(cudaMemcpyAsync(dst, c->h_stage, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return;
   }
-  launch_gather2(c, src, c->d_n2u, dst, n);
+  // stage[2] and stage[3] are contiguous (allocated as one block)
+  CUDA_OK(cudaMemcpyAsync(c->stage[2], user, 2 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_gather2(c, (const double2*)c->stage[2], c->d_n2u, dst, n);
 }
-// internal-order device vector -> caller array (synchronous for host destinations)
+// local-order device vector -> caller array (synchronous for host destinations).
+// Distributed contexts write the OWNED entries only (the caller's array is global-sized).
 void export_vec(cfem_ctx* c, const double* internal, double* user) {
+  if (c->world > 1) {
+    const int64_t no = c->dm.no;
+    if (is_device_ptr(user)) { launch_scatter(c, internal, c->d_n2u, user, no); return; }
+    CUDA_OK(cudaMemcpyAsync(c->h_stage, internal, no * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    const int32_t* n2u = c->hm.n2u.data();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < no; ++i) user[n2u[i]] = c->h_stage[i];
+    return;
+  }
   const int64_t n = c->dm.nn;
   if (is_device_ptr(user)) {
     launch_gather(c, internal, c->d_u2n, user, n);
@@ -98,27 +124,35 @@ void import_bc(cfem_ctx* c, const double* bc_values) {
   if (!bc_values) { launch_bc_values(c, CFEM_BC_CONSTANT, 0.0, 0.0, nullptr, c->g); return; }
   const double* src = bc_values;
   if (!is_device_ptr(bc_values)) {
-    CUDA_OK(cudaMemcpyAsync(c->stage[0], bc_values, c->nbc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->stage[0], bc_values, c->nbc_user * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     src = c->stage[0];
   }
   launch_bc_values(c, CFEM_BC_USER, 0.0, 0.0, src, c->g);
 }
 
 void apply_dirichlet(cfem_ctx* c, const int32_t* dofs, int64_t n) {
-  const int64_t nn = c->dm.nn;
-  std::vector<uint8_t> flag(nn, 0);
-  std::vector<int32_t> nodes(n);
+  const int64_t nl = c->dm.nn;
+  std::vector<uint8_t> flag(nl, 0);
+  std::vector<int32_t> nodes, pos;
   c->bc_user.assign(dofs, dofs + n);
   for (int64_t j = 0; j < n; ++j) {
-    if (dofs[j] < 0 || dofs[j] >= nn) CFEM_THROW(-1, "Dirichlet dof out of range");
-    nodes[j] = c->hm.u2n[dofs[j]];
-    flag[nodes[j]] = 1;
+    if (dofs[j] < 0 || dofs[j] >= c->hm.nn_global) CFEM_THROW(-1, "Dirichlet dof out of range");
+    const int32_t l = user_to_local(c->hm, dofs[j]);
+    if (l < 0) continue;  // held by another rank
+    nodes.push_back(l);
+    pos.push_back((int32_t)j);
+    flag[l] = 1;
   }
-  CUDA_OK(cudaMemcpy(c->d_is_bc, flag.data(), nn, cudaMemcpyHostToDevice));
-  if (n > 0) CUDA_OK(cudaMemcpy(c->d_bc_nodes, nodes.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
-  c->nbc = n;
+  if (n > 2 * nl && c->world == 1) CFEM_THROW(-1, "Dirichlet list longer than the mesh");
+  CUDA_OK(cudaMemcpy(c->d_is_bc, flag.data(), nl, cudaMemcpyHostToDevice));
+  if (!nodes.empty()) {
+    CUDA_OK(cudaMemcpy(c->d_bc_nodes, nodes.data(), nodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->d_bc_pos, pos.data(), pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  c->nbc = (int64_t)nodes.size();
+  c->nbc_user = n;
   launch_mass(c, c->mat[CFEM_MAT_MASS_BC], true);
-  launch_fill(c, c->g, 0.0, nn);
+  launch_fill(c, c->g, 0.0, nl);
 }
 
 Matrix& get_matrix(cfem_ctx* c, int which) {
@@ -128,12 +162,13 @@ Matrix& get_matrix(cfem_ctx* c, int which) {
 }
 
 void build_user_csr(cfem_ctx* c) {
+  if (c->world > 1) CFEM_THROW(-1, "the global CSR pattern / matrix export is not available in a distributed context");
   if (!c->u_rowptr.empty()) return;
   const HostMesh& hm = c->hm;
   const int64_t nn = hm.nn;
   c->u_rowptr.assign(nn + 1, 0);
   for (int64_t u = 0; u < nn; ++u) {
-    const int32_t i = hm.u2n[u];
+    const int32_t i = hm.u2n[u];  // world == 1: global == local
     c->u_rowptr[u + 1] = c->u_rowptr[u] + (hm.rowptr[i + 1] - hm.rowptr[i]);
   }
   c->u_colidx.resize(hm.nnz);
@@ -184,8 +219,9 @@ int cfem_device_count(void) {
   return n;
 }
 
-int cfem_create(cfem_ctx** out, int device, int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
-                const void* cells, int cell_index_bytes, int order) {
+static int create_impl(cfem_ctx** out, int device, int rank, int world, const void* nccl_id, int64_t n_nodes,
+                       int64_t n_cells, const double* x, int xdim, const void* cells, int cell_index_bytes,
+                       int order) {
   cfem_ctx* c = nullptr;
   API_BEGIN
   if (!out || !x || !cells) CFEM_THROW(-1, "null argument");
@@ -203,11 +239,13 @@ int cfem_create(cfem_ctx** out, int device, int64_t n_nodes, int64_t n_cells, co
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  analyse_mesh(c->hm, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order);
+  if (world > 1 && !nccl_id) CFEM_THROW(-1, "distributed context needs the NCCL unique id");
+  analyse_mesh(c->hm, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order, rank, world);
+  comm_init(c, rank, world, nccl_id);
   HostMesh& hm = c->hm;
   const int64_t nn = hm.nn;
   DevMesh& dm = c->dm;
-  dm.nn = nn; dm.nc = hm.nc; dm.nnz = hm.nnz;
+  dm.nn = nn; dm.nc = hm.nc; dm.nnz = hm.nnz; dm.no = hm.n_owned; dm.nn_global = hm.nn_global;
   dm.ntiles = (int)hm.tile_node.size() - 1;
   dm.xy = (const double2*)upload(c, hm.xy);
   dm.cells = upload(c, hm.cells);
@@ -219,17 +257,21 @@ int cfem_create(cfem_ctx** out, int device, int64_t n_nodes, int64_t n_cells, co
   dm.tile_cellptr = upload(c, hm.tile_cellptr);
   dm.tile_cells = upload(c, hm.tile_cells);
   c->d_n2u = upload(c, hm.n2u);
-  c->d_u2n = upload(c, hm.u2n);
+  c->d_u2n = world == 1 ? upload(c, hm.u2n) : nullptr;  // user -> local is only a permutation on one GPU
+  c->d_send_idx = upload(c, hm.send_idx);
+  c->d_sendbuf = dalloc<double>(c, 2 * (int64_t)hm.send_idx.size());
   c->d_is_bnd = upload(c, hm.is_bnd);
   c->d_is_bc = dalloc<uint8_t>(c, nn);
   dm.is_bc = c->d_is_bc;
   c->d_bc_nodes = dalloc<int32_t>(c, nn);
+  c->d_bc_pos = dalloc<int32_t>(c, nn);
   // host-side copies that are only needed on the device from here on
   std::vector<double>().swap(hm.xy);
   std::vector<int32_t>().swap(hm.cells);
   std::vector<uint32_t>().swap(hm.v2c_code);
   std::vector<int32_t>().swap(hm.v2c_ptr);
   std::vector<int32_t>().swap(hm.tile_cells);
+  if (world > 1) CUDA_OK(cudaMallocHost((void**)&c->h_stage, 2 * nn * sizeof(double)));
   for (int k = 0; k < 4; ++k) {
     c->mat[k].vals = dalloc<double>(c, hm.nnz);
     c->mat[k].dinv = dalloc<double>(c, nn);
@@ -262,10 +304,39 @@ int cfem_create(cfem_ctx** out, int device, int64_t n_nodes, int64_t n_cells, co
   catch (const std::exception& e) { cfem::set_error(e.what()); if (c) cfem_destroy(c); return -9; }
 }
 
+int cfem_create(cfem_ctx** out, int device, int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
+                const void* cells, int cell_index_bytes, int order) {
+  return create_impl(out, device, 0, 1, nullptr, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order);
+}
+
+int cfem_nccl_unique_id(void* out128) {
+  API_BEGIN
+  if (!out128) CFEM_THROW(-1, "null argument");
+  comm_unique_id(out128);
+  API_END
+}
+
+int cfem_create_distributed(cfem_ctx** out, int device, int rank, int world, const void* nccl_id128,
+                            int64_t n_nodes, int64_t n_cells, const double* x, int xdim, const void* cells,
+                            int cell_index_bytes, int order) {
+  return create_impl(out, device, rank, world, nccl_id128, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order);
+}
+
+int64_t cfem_num_owned(const cfem_ctx* c) { return c->dm.no; }
+int64_t cfem_num_ghosts(const cfem_ctx* c) { return c->dm.nn - c->dm.no; }
+int cfem_comm_stats(const cfem_ctx* c, int64_t* halo_exchanges, int64_t* allreduces, int64_t* halo_doubles_sent) {
+  if (halo_exchanges) *halo_exchanges = c->halo_exchanges;
+  if (allreduces) *allreduces = c->allreduces;
+  if (halo_doubles_sent) *halo_doubles_sent = (int64_t)c->hm.send_idx.size();
+  return 0;
+}
+
 void cfem_destroy(cfem_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  comm_destroy(c);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   for (void* p : c->allocs) cudaFree(p);
   for (cudaEvent_t e : c->prof.ev) cudaEventDestroy(e);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -280,11 +351,11 @@ int cfem_synchronize(cfem_ctx* c) {
   API_END
 }
 
-int64_t cfem_num_nodes(const cfem_ctx* c) { return c->dm.nn; }
+int64_t cfem_num_nodes(const cfem_ctx* c) { return c->dm.nn_global; }
 int64_t cfem_num_cells(const cfem_ctx* c) { return c->dm.nc; }
 int64_t cfem_num_nonzeros(const cfem_ctx* c) { return c->dm.nnz; }
 int64_t cfem_num_boundary(const cfem_ctx* c) { return (int64_t)c->hm.bnd_user_sorted.size(); }
-int64_t cfem_num_dirichlet(const cfem_ctx* c) { return c->nbc; }
+int64_t cfem_num_dirichlet(const cfem_ctx* c) { return c->nbc_user; }
 int64_t cfem_num_tiles(const cfem_ctx* c) { return c->dm.ntiles; }
 int64_t cfem_device_bytes(const cfem_ctx* c) { return c->bytes; }
 
@@ -313,6 +384,7 @@ int cfem_set_dirichlet(cfem_ctx* c, const int32_t* dofs, int64_t n) {
 
 int cfem_get_ordering(cfem_ctx* c, int32_t* n2u) {
   API_BEGIN
+  // distributed: the first cfem_num_owned entries are the owned dofs, then the ghosts
   std::memcpy(n2u, c->hm.n2u.data(), c->hm.n2u.size() * sizeof(int32_t));
   API_END
 }
@@ -499,7 +571,8 @@ int cfem_state_get(cfem_ctx* c, double* uh, double* u_n, double* u_old, double* 
 }
 
 // sqrt(sum of the per-CTA partials) on the host (one sync)
-static double partials_norm(cfem_ctx* c, const double* part, int npart) {
+static double partials_norm(cfem_ctx* c, double* part, int npart) {
+  npart = allreduce_sum1(c, part, npart);
   double* tmp = c->h_pinned + 64;
   CUDA_OK(cudaMemcpyAsync(tmp, part, npart * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -527,8 +600,8 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
     if (!bc_values) CFEM_THROW(-1, "step_scalar: CFEM_BC_USER needs bc_values");
     if (is_device_ptr(bc_values)) d_bc_user = bc_values;
     else {
-      if ((int64_t)n_steps * c->nbc > 2 * nn) CFEM_THROW(-1, "step_scalar: too many user bc values for one call");
-      CUDA_OK(cudaMemcpyAsync(c->stage[2], bc_values, (size_t)n_steps * c->nbc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      if ((int64_t)n_steps * c->nbc_user > 2 * nn) CFEM_THROW(-1, "step_scalar: too many user bc values for one call");
+      CUDA_OK(cudaMemcpyAsync(c->stage[2], bc_values, (size_t)n_steps * c->nbc_user * sizeof(double), cudaMemcpyHostToDevice, c->stream));
       d_bc_user = c->stage[2];
     }
   }
@@ -539,7 +612,7 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
   Matrix& J = c->mat[CFEM_MAT_SYSTEM];
   for (int s = 0; s < n_steps; ++s) {
     c->t += p->dt;
-    launch_bc_values(c, p->bc_kind, p->bc_value, c->t, d_bc_user ? d_bc_user + (int64_t)s * c->nbc : nullptr, c->g);
+    launch_bc_values(c, p->bc_kind, p->bc_value, c->t, d_bc_user ? d_bc_user + (int64_t)s * c->nbc_user : nullptr, c->g);
     // (a-3) residual projection  M_bc RH = b
     launch_rv_rhs(c, p->flux, p->scheme, p->dt, c->u_n, c->u_old, c->u_oo, nullptr, true, b, c->fluxn);
     SolveResult rm = mass_solve(c, p->mass_solver, c->mat[CFEM_MAT_MASS_BC], b, c->RH, p->lin_rtol, p->lin_max_it, &c->pcg_predict);
@@ -559,7 +632,8 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
       SolveResult rk = run_solver(c, p->solver, J, F, dx, p->lin_rtol, 0.0, p->lin_max_it, &c->krylov_predict);
       if (!rk.converged) CFEM_THROW(-3, "step_scalar: Krylov solve did not converge (relres " + std::to_string(rk.relres) + ")");
       st.krylov_iterations += rk.iters;
-      launch_sub(c, c->uh, dx, nn);
+      launch_sub(c, c->uh, dx, c->dm.no);
+      halo_exchange(c, c->uh);
       ++it;
       np = launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, c->fluxn, F, normpart);
       res = partials_norm(c, normpart, np);
@@ -751,6 +825,11 @@ static auto host_array(const cfem_host_mesh* h, int what, F&& f) {
     case CFEM_HM_TILE_CELLS: return f(m.tile_cells.data(), m.tile_cells.size(), 4);
     case CFEM_HM_IS_BND: return f(m.is_bnd.data(), m.is_bnd.size(), 1);
     case CFEM_HM_BND_USER: return f(m.bnd_user_sorted.data(), m.bnd_user_sorted.size(), 4);
+    case CFEM_HM_PEER_RANK: return f(m.peer_rank.data(), m.peer_rank.size(), 4);
+    case CFEM_HM_SEND_PTR: return f(m.send_ptr.data(), m.send_ptr.size(), 4);
+    case CFEM_HM_SEND_IDX: return f(m.send_idx.data(), m.send_idx.size(), 4);
+    case CFEM_HM_RECV_OFF: return f(m.recv_off.data(), m.recv_off.size(), 4);
+    case CFEM_HM_RECV_CNT: return f(m.recv_cnt.data(), m.recv_cnt.size(), 4);
     default: return f(nullptr, (size_t)0, 0);
   }
 }
@@ -770,6 +849,29 @@ int cfem_host_analyse(cfem_host_mesh** out, int64_t n_nodes, int64_t n_cells, co
   catch (const std::exception& e) { cfem::set_error(e.what()); delete h; return -9; }
 }
 
+int cfem_host_analyse_part(cfem_host_mesh** out, int rank, int world, int64_t n_nodes, int64_t n_cells,
+                           const double* x, int xdim, const void* cells, int cell_index_bytes, int order) {
+  cfem_host_mesh* h = nullptr;
+  try {
+    if (!out || !x || !cells) CFEM_THROW(-1, "null argument");
+    h = new cfem_host_mesh();
+    analyse_mesh(h->hm, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order, rank, world);
+    *out = h;
+    return 0;
+  } catch (const cfem::Error& e) { cfem::set_error(e.msg); delete h; return e.code; }
+  catch (const std::exception& e) { cfem::set_error(e.what()); delete h; return -9; }
+}
+int64_t cfem_host_info(const cfem_host_mesh* h, int what) {
+  const HostMesh& m = h->hm;
+  switch (what) {
+    case 0: return m.n_owned;
+    case 1: return m.nn;
+    case 2: return m.nn_global;
+    case 3: return m.nc;
+    case 4: return m.nnz;
+    default: return -1;
+  }
+}
 int64_t cfem_host_size(const cfem_host_mesh* h, int what) {
   return host_array(h, what, [](const void*, size_t n, int) { return (int64_t)n; });
 }

@@ -35,9 +35,19 @@ constexpr int kTileNnzCap = 2560;    // CSR entries of a tile's rows staged in s
 
 // Host-side result of the mesh analysis (setup.cpp). All ids internal unless
 // suffixed _user.
+// In a distributed context (world > 1) "internal" ids are LOCAL: owned nodes first (a contiguous
+// range [part_off[rank], part_off[rank+1]) of the global Hilbert order), then the ghost layer in
+// ascending global order (hence grouped by owner rank).
 struct HostMesh {
-  int64_t nn = 0, nc = 0, nnz = 0;
-  std::vector<int32_t> n2u, u2n;          // internal->user, user->internal
+  int64_t nn = 0, nc = 0, nnz = 0;        // local nodes (owned + ghosts), local cells, nnz of owned rows
+  int64_t n_owned = 0, nn_global = 0;
+  int rank = 0, world = 1;
+  std::vector<int64_t> part_off;          // world+1 offsets into the global Hilbert order
+  std::vector<int32_t> ghost_global;      // global internal ids of the ghosts, ascending
+  std::vector<int32_t> peer_rank;         // ranks we exchange with
+  std::vector<int32_t> send_ptr, send_idx;  // per peer: owned local ids whose values the peer ghosts
+  std::vector<int32_t> recv_off, recv_cnt;  // per peer: where its values land in the ghost segment
+  std::vector<int32_t> n2u, u2n;          // local->user ; user->GLOBAL internal
   std::vector<double> xy;                 // 2*nn, internal order
   std::vector<int32_t> cells;             // 3*nc, internal ids, internal cell order
   std::vector<int32_t> rowptr, colidx;    // P1 pattern == node patches
@@ -52,11 +62,15 @@ struct HostMesh {
 };
 
 void analyse_mesh(HostMesh& hm, int64_t nn, int64_t nc, const double* x, int xdim,
-                  const void* cells, int idx_bytes, int order);
+                  const void* cells, int idx_bytes, int order, int rank = 0, int world = 1);
+// user dof -> local id (owned or ghost) or -1 if this rank does not hold it
+int32_t user_to_local(const HostMesh& hm, int64_t user_dof);
 
 // Device view handed to kernels by value.
 struct DevMesh {
-  int64_t nn, nc, nnz;
+  int64_t nn, nc, nnz;     // local nodes (owned + ghosts), local cells, nnz of owned rows
+  int64_t no;              // owned nodes == rows; == nn on a single GPU
+  int64_t nn_global;
   int ntiles;
   const double2* xy;
   const int32_t* cells;
@@ -83,7 +97,7 @@ struct Launches {  // counters of our own kernel launches
 };
 
 // Optional per-launch CUDA-event bracketing (bench.py roofline leg).
-enum { PROF_SPMV = 0, PROF_ASM_VEC = 1, PROF_ASM_MAT = 2, PROF_KRYLOV_VEC = 3, PROF_RV = 4, PROF_MISC = 5, PROF_CHEB = 6, PROF_NCAT = 8 };
+enum { PROF_SPMV = 0, PROF_ASM_VEC = 1, PROF_ASM_MAT = 2, PROF_KRYLOV_VEC = 3, PROF_RV = 4, PROF_MISC = 5, PROF_CHEB = 6, PROF_COMM = 7, PROF_NCAT = 8 };
 struct Profiler {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs
@@ -114,8 +128,10 @@ struct cfem_ctx {
   int64_t bytes = 0;
   int32_t *d_n2u = nullptr, *d_u2n = nullptr;
   uint8_t *d_is_bc = nullptr, *d_is_bnd = nullptr;
-  int32_t* d_bc_nodes = nullptr;  // internal ids, in caller's Dirichlet order
-  int64_t nbc = 0;
+  int32_t* d_bc_nodes = nullptr;  // local ids of the Dirichlet nodes this rank holds (owned or ghost)
+  int32_t* d_bc_pos = nullptr;    // their position in the caller's Dirichlet list (CFEM_BC_USER values)
+  int64_t nbc = 0;                // held locally
+  int64_t nbc_user = 0;           // size of the caller's list
   std::vector<int32_t> bc_user;   // caller's Dirichlet set
   cfem::Matrix mat[4];
   // state vectors (internal order)
@@ -134,6 +150,13 @@ struct cfem_ctx {
   // user-order CSR export (lazy)
   std::vector<int32_t> u_rowptr, u_colidx, u_slot;
   cfem::Launches launches;
+  // ---- distributed (world > 1): NCCL communicator + halo buffers
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+  int32_t* d_send_idx = nullptr;
+  double* d_sendbuf = nullptr;      // 2 * total send count (double2 exchanges)
+  double* h_stage = nullptr;        // pinned host staging, 2 * nn doubles
+  int64_t halo_exchanges = 0, allreduces = 0;
   cfem::Profiler prof;
   int pcg_predict = 28, krylov_predict = 8;
 };

@@ -28,6 +28,7 @@ int assembly_grid(const cfem_ctx* c);
 // ---- linear algebra (linalg.cu) ------------------------------------------------
 void launch_spmv(cfem_ctx* c, const Matrix& A, const double* x, double* y);
 void launch_gather(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n);      // dst[i] = src[idx[i]]
+void launch_scatter(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n);     // dst[idx[i]] = src[i]
 void launch_gather2(cfem_ctx* c, const double2* src, const int32_t* idx, double2* dst, int64_t n);
 void launch_fill(cfem_ctx* c, double* dst, double v, int64_t n);
 void launch_copy(cfem_ctx* c, double* dst, const double* src, int64_t n);
@@ -44,6 +45,15 @@ SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, d
 SolveResult gmres(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol,
                   double atol, int max_it, int* predict);
 double norm2(cfem_ctx* c, const double* v, int64_t n);  // synchronous
+
+// ---- multi-GPU (comm.cu); every call is a no-op when world == 1 --------------------
+void comm_unique_id(void* out128);
+void comm_init(cfem_ctx* c, int rank, int world, const void* id128);
+void comm_destroy(cfem_ctx* c);
+void halo_exchange(cfem_ctx* c, double* v, int width = 1);
+// local reduce of each partial array to its element 0 + all-reduce; returns the partial count to use after
+int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int* ops /*0 sum,1 min,2 max*/, int npart);
+int allreduce_sum1(cfem_ctx* c, double* slot, int npart);
 
 // ---- RV (rv.cu) ------------------------------------------------------------------
 // sum / min / max of v -> c->scalars[0..2] (device), no host sync

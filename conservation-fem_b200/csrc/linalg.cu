@@ -56,6 +56,13 @@ __global__ void k_sum_partials(const double* __restrict__ partials, int n, doubl
   if (threadIdx.x == 0) *out = s;
 }
 
+__global__ void k_scatter(const double* __restrict__ src, const int32_t* __restrict__ idx, double* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) dst[idx[i]] = src[i];
+}
+void launch_scatter(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n) {
+  ProfScope ps(c, PROF_MISC);
+  k_scatter<<<vec_grid(c, n), kBlock, 0, c->stream>>>(src, idx, dst, n); LAUNCHED(c);
+}
 void launch_gather(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n) {
   ProfScope ps(c, PROF_MISC);
   k_gather<<<vec_grid(c, n), kBlock, 0, c->stream>>>(src, idx, dst, n); LAUNCHED(c);
@@ -198,23 +205,29 @@ static inline int spmv_grid(const cfem_ctx* c) {
   const int64_t cap = (int64_t)c->sm_count * 8;
   if (spmv_mode() == 0) return (int)(c->dm.ntiles < cap ? c->dm.ntiles : cap);
   const int64_t rows_per_block = (kBlock / 32) * 4;
-  int64_t b = (c->dm.nn + rows_per_block - 1) / rows_per_block;
+  int64_t b = (c->dm.no + rows_per_block - 1) / rows_per_block;
   return (int)(b < cap ? b : cap);
 }
 
 template <int NDOT>
 static void spmv_dots(cfem_ctx* c, const Matrix& A, const double* x, double* y, const double* d0,
                       const double* d1, double* p0, double* p1, bool gated) {
+  halo_exchange(c, const_cast<double*>(x));  // ghosts of the input vector (no-op on one GPU)
   ProfScope ps(c, PROF_SPMV);
   if (spmv_mode() == 0)
     k_spmv_stream<NDOT><<<spmv_grid(c), kTileNodes, 0, c->stream>>>(c->dm.ntiles, c->dm.tile_node, c->dm.rowptr,
                                                                     c->dm.colidx, A.vals, x, y, d0, d1, p0, p1,
                                                                     gated ? c->status : nullptr);
   else
-    k_spmv<8, NDOT><<<spmv_grid(c), kBlock, 0, c->stream>>>(c->dm.nn, c->dm.rowptr, c->dm.colidx, A.vals, x, y, d0,
+    k_spmv<8, NDOT><<<spmv_grid(c), kBlock, 0, c->stream>>>(c->dm.no, c->dm.rowptr, c->dm.colidx, A.vals, x, y, d0,
                                                             d1, p0, p1, gated ? c->status : nullptr);
   LAUNCHED(c);
   c->launches.spmv++;
+  if (c->world > 1 && NDOT >= 1) {
+    double* sl[2] = {p0, p1};
+    const int op[2] = {0, 0};
+    allreduce_partials(c, NDOT, sl, op, spmv_grid(c));
+  }
 }
 
 void launch_spmv(cfem_ctx* c, const Matrix& A, const double* x, double* y) {
@@ -282,16 +295,17 @@ k_cheb_stream(const int ntiles, const int32_t* __restrict__ tile_node, const int
 
 // writes sqrt(rr/bb) to scalars[S_RELRES] from the partials
 __global__ void __launch_bounds__(kBlock)
-k_relres(const double* __restrict__ part, int npart, double* __restrict__ scalars) {
+k_relres(const double* __restrict__ part, int npart_rr, int npart_bb, double* __restrict__ scalars) {
   __shared__ double red[9];
-  const double rr = reduce_partials(part + P_RR * kMaxPartials, npart, red);
-  const double bb = reduce_partials(part + P_BB * kMaxPartials, npart, red);
+  const double rr = reduce_partials(part + P_RR * kMaxPartials, npart_rr, red);
+  const double bb = reduce_partials(part + P_BB * kMaxPartials, npart_bb, red);
   if (threadIdx.x == 0) { scalars[S_RR] = rr; scalars[S_BB] = bb; scalars[S_RELRES] = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr); }
 }
 
 SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, int max_it,
                            int* predict) {
-  const int64_t n = c->dm.nn;
+  const int64_t n = c->dm.nn;  // copies move ghosts too
+  int np_bb = 0;
   double *xa = x, *xb = c->wk[0], *d = c->wk[1];
   double* part = c->partials;
   const int gs = spmv_grid(c);
@@ -305,6 +319,7 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
   if (target > max_it) target = max_it;
   while (true) {
     for (; it < target; ++it) {
+      halo_exchange(c, xa);
       ProfScope ps(c, PROF_CHEB);
       if (it == 0) {
         k_cheb_stream<true><<<gs, kTileNodes, 0, c->stream>>>(c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
@@ -319,10 +334,12 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
       }
       LAUNCHED(c);
       c->launches.spmv++;
+      if (it == 0) np_bb = allreduce_sum1(c, part + P_BB * kMaxPartials, gs);
       std::swap(xa, xb);
     }
     // the last kernel measured ||b - M x_{it-1}||; x_it is one update further on
-    { ProfScope ps(c, PROF_KRYLOV_VEC); k_relres<<<1, kBlock, 0, c->stream>>>(part, gs, c->scalars); LAUNCHED(c); }
+    const int np_rr = allreduce_sum1(c, part + P_RR * kMaxPartials, gs);
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_relres<<<1, kBlock, 0, c->stream>>>(part, np_rr, np_bb, c->scalars); LAUNCHED(c); }
     CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + S_RELRES, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     res.iters = it;
@@ -337,6 +354,7 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
     if (target > max_it) target = max_it;
   }
   if (xa != x) launch_copy(c, x, xa, n);
+  halo_exchange(c, x);  // the solution leaves with valid ghosts
   if (predict) {
     // next solve: drop the iterations the achieved residual shows were not needed (keep one spare)
     int spare = (res.converged && res.relres > 0.0) ? (int)floor(log(rtol / res.relres) / log(3.0)) - 1 : 0;
@@ -446,21 +464,26 @@ static bool poll_done(cfem_ctx* c, SolveResult& res) {
 
 SolveResult pcg(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
                 int max_it, int* predict) {
-  const int64_t n = c->dm.nn;
+  const int64_t n = c->dm.no;
+  const bool dist = c->world > 1;
   double *r = c->wk[0], *z = c->wk[1], *p = c->wk[2], *q = c->wk[3];
   double* part = c->partials;
   const int gv = vec_grid(c, n), gs = spmv_grid(c);
+  const int npv = dist ? 1 : gv, nps = dist ? 1 : gs;  // partial counts seen by consumers
+  const int sum2[3] = {0, 0, 0};
   const double rtol2 = rtol * rtol, atol2 = atol * atol;
   launch_spmv(c, A, x, q);
   { ProfScope ps(c, PROF_KRYLOV_VEC); k_pcg_init<<<gv, kBlock, 0, c->stream>>>(n, b, q, A.dinv, r, z, p, part, c->status); LAUNCHED(c); }
-  { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
+  { double* sl[3] = {part + P_RZ0 * kMaxPartials, part + P_RR * kMaxPartials, part + P_BB * kMaxPartials}; allreduce_partials(c, 3, sl, sum2, gv); }
+  { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, npv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
   SolveResult res{0, 0.0, false};
   int it = 0, next_poll = predict ? (*predict > 2 ? *predict - 1 : 1) : 4;
   while (it < max_it) {
     const int cur = it & 1;
     spmv_dots<1>(c, A, p, q, p, nullptr, part + P_PQ * kMaxPartials, nullptr, true);
-    { ProfScope ps(c, PROF_KRYLOV_VEC); k_pcg_update<<<gv, kBlock, 0, c->stream>>>(n, p, q, A.dinv, x, r, z, part, gs, gv, cur, c->status); LAUNCHED(c); }
-    { ProfScope ps(c, PROF_KRYLOV_VEC); k_pcg_p<<<gv, kBlock, 0, c->stream>>>(n, z, p, part, gv, cur, c->scalars, c->status, rtol2, atol2); LAUNCHED(c); }
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_pcg_update<<<gv, kBlock, 0, c->stream>>>(n, p, q, A.dinv, x, r, z, part, nps, npv, cur, c->status); LAUNCHED(c); }
+    { double* sl[2] = {part + (cur ? P_RZ0 : P_RZ1) * kMaxPartials, part + P_RR * kMaxPartials}; allreduce_partials(c, 2, sl, sum2, gv); }
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_pcg_p<<<gv, kBlock, 0, c->stream>>>(n, z, p, part, npv, cur, c->scalars, c->status, rtol2, atol2); LAUNCHED(c); }
     ++it;
     if (it >= next_poll || it == max_it) {
       if (poll_done(c, res)) break;
@@ -468,6 +491,7 @@ SolveResult pcg(cfem_ctx* c, const Matrix& A, const double* b, double* x, double
     }
   }
   if (!res.converged) poll_done(c, res);
+  halo_exchange(c, x);
   if (predict) *predict = res.iters > 0 ? res.iters : 1;
   return res;
 }
@@ -567,36 +591,42 @@ k_bi_x(int64_t n, const double* __restrict__ y, const double* __restrict__ z, co
 
 SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
                      int max_it, int* predict) {
-  const int64_t n = c->dm.nn;
+  const int64_t n = c->dm.no;
+  const bool dist = c->world > 1;
   double *r = c->wk[0], *rhat = c->wk[1], *p = c->wk[2], *v = c->wk[3], *s = c->wk[4], *t = c->wk[5],
          *y = c->wk[6], *z = c->wk[7];
   double* part = c->partials;
   const int gv = vec_grid(c, n), gs = spmv_grid(c);
   const double rtol2 = rtol * rtol, atol2 = atol * atol;
+  const int npv = dist ? 1 : gv, nps = dist ? 1 : gs;
+  const int sum3[3] = {0, 0, 0};
   launch_spmv(c, A, x, v);
   { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_init<<<gv, kBlock, 0, c->stream>>>(n, b, v, A.dinv, r, rhat, p, y, part, c->status); LAUNCHED(c); }
-  { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
+  { double* sl[3] = {part + P_RR * kMaxPartials, part + P_RZ0 * kMaxPartials, part + P_BB * kMaxPartials}; allreduce_partials(c, 3, sl, sum3, gv); }
+  { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, npv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
   SolveResult res{0, 0.0, false};
   int it = 0, next_poll = predict ? (*predict > 2 ? *predict - 1 : 1) : 4;
   while (it < max_it) {
     const int cur = it & 1;  // rho of this iteration lives in RZ[cur]
     if (it > 0) {
-      { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_p<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, p, y, part, gv, cur, c->scalars, c->status, rtol2, atol2);
+      { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_p<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, p, y, part, npv, cur, c->scalars, c->status, rtol2, atol2);
       LAUNCHED(c); }
     }
     spmv_dots<1>(c, A, y, v, rhat, nullptr, part + P_PQ * kMaxPartials, nullptr, true);
-    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_s<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, s, z, part, gv, gs, cur, c->scalars, c->status); LAUNCHED(c); }
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_s<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, s, z, part, npv, nps, cur, c->scalars, c->status); LAUNCHED(c); }
     spmv_dots<2>(c, A, z, t, s, t, part + P_A * kMaxPartials, part + P_B * kMaxPartials, true);
-    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_x<<<gv, kBlock, 0, c->stream>>>(n, y, z, s, t, rhat, x, r, part, gs, cur, c->scalars, c->status); LAUNCHED(c); }
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_x<<<gv, kBlock, 0, c->stream>>>(n, y, z, s, t, rhat, x, r, part, nps, cur, c->scalars, c->status); LAUNCHED(c); }
+    { double* sl[2] = {part + (cur ? P_RZ0 : P_RZ1) * kMaxPartials, part + P_RR * kMaxPartials}; allreduce_partials(c, 2, sl, sum3, gv); }
     ++it;
     if (it >= next_poll || it == max_it) {
       // the convergence test for iteration `it` runs inside the next k_bi_p; issue a stand-alone check
-      { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, gv, c->scalars, c->status, rtol2, atol2, 0, it); LAUNCHED(c); }
+      { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, npv, c->scalars, c->status, rtol2, atol2, 0, it); LAUNCHED(c); }
       if (poll_done(c, res)) break;
       next_poll = it + 2;
     }
   }
   if (!res.converged) { poll_done(c, res); }
+  halo_exchange(c, x);
   if (predict) *predict = res.iters > 0 ? res.iters : 1;
   return res;
 }

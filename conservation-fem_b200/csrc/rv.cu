@@ -31,12 +31,14 @@ __device__ __forceinline__ double beta_of(double u) {
 // one pass: partial sum / min / max of v; optionally beta[i] = ||f'(v_i)||
 template <int FLUX>
 __global__ void __launch_bounds__(kBlock)
-k_stats(int64_t n, const double* __restrict__ v, double* __restrict__ beta, double* __restrict__ part) {
+k_stats(int64_t n_owned, int64_t n_local, const double* __restrict__ v, double* __restrict__ beta,
+        double* __restrict__ part) {
   __shared__ double red[9];
   double s = 0.0, mn = INFINITY, mx = -INFINITY;
+  const int64_t n = FLUX >= 0 ? n_local : n_owned;  // beta is also needed on the ghosts
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
     const double x = v[i];
-    s += x; mn = fmin(mn, x); mx = fmax(mx, x);
+    if (i < n_owned) { s += x; mn = fmin(mn, x); mx = fmax(mx, x); }
     if (FLUX >= 0) beta[i] = beta_of<FLUX>(x);
   }
   s = block_sum(s, red); mn = block_min(mn, red); mx = block_max(mx, red);
@@ -63,55 +65,8 @@ __device__ __forceinline__ double absolute_term(const double* part, int npart, i
 // Python min(a, b): b if b < a else a  (NaN / inf second argument keeps a)
 __device__ __forceinline__ double pymin(double a, double b) { return b < a ? b : a; }
 
-// RV.get_epsilon_nonlinear (RV.py:56-90) / get_epsilon_linear (RV.py:92-127)
-template <int LANES, bool LINEAR>
-__global__ void __launch_bounds__(kBlock)
-k_epsilon_patch(const int64_t nn, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                const double* __restrict__ u_n, const double* __restrict__ Rh, const double* __restrict__ beta,
-                const double2* __restrict__ w, const double* __restrict__ h, const double* __restrict__ part,
-                int npart, double Cvel, double Crv, double* __restrict__ eps) {
-  __shared__ double red[9];
-  const double A = absolute_term(part, npart, nn, red);
-  constexpr int RPW = 32 / LANES;
-  const int lane = threadIdx.x & 31, sub = lane / LANES, sl = lane % LANES;
-  const int64_t warp = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
-  for (int64_t base = warp * RPW; base < nn; base += nwarps * RPW) {
-    const int64_t row = base + sub;
-    double umax = -INFINITY, umin = INFINITY, rmax = 0.0, bmax = 0.0;
-    if (row < nn) {
-      const int p1 = rowptr[row + 1];
-      for (int p = rowptr[row] + sl; p < p1; p += LANES) {
-        const int j = colidx[p];
-        const double uj = u_n[j];
-        umax = fmax(umax, uj); umin = fmin(umin, uj);
-        rmax = fmax(rmax, fabs(Rh[j]));
-        if (!LINEAR) bmax = fmax(bmax, beta[j]);
-      }
-    }
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) {
-      umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
-      umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-      rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-      if (!LINEAR) bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-    }
-    if (sl == 0 && row < nn) {
-      if (LINEAR) {
-        const double2 wi = w[row];  // centre node, RV.py:113-115
-        bmax = sqrt(__dadd_rn(__dmul_rn(wi.x, wi.x), __dmul_rn(wi.y, wi.y)));
-      }
-      const double hi = h[row];
-      const double n_i = fabs((umax - umin) - A);
-      const double Ri = rmax / n_i;
-      const double first = __dmul_rn(__dmul_rn(Cvel, hi), bmax);
-      const double second = __dmul_rn(__dmul_rn(Crv, __dmul_rn(hi, hi)), fabs(Ri));
-      eps[row] = pymin(first, second);
-    }
-  }
-}
-
-// Tile-streamed form of the same computation: the tile's column indices are staged in
+// RV.get_epsilon_nonlinear (RV.py:56-90) / get_epsilon_linear (RV.py:92-127).
+// Tile-streamed: the tile's column indices are staged in
 // shared memory once (coalesced), then three coalesced gather passes (u_n, |Rh|, beta)
 // park values in shared memory and thread r reduces row r's patch.
 template <bool LINEAR>
@@ -168,12 +123,12 @@ k_epsilon_stream(const int ntiles, const int64_t nn, const int32_t* __restrict__
 // get_epsilon_linear_simple (RV.py:129-142; also normalises Rh in place)
 template <int FLUX>
 __global__ void __launch_bounds__(kBlock)
-k_epsilon_pointwise(int64_t n, int variant, const double* __restrict__ uh, double* __restrict__ Rh,
+k_epsilon_pointwise(int64_t n, int64_t n_global, int variant, const double* __restrict__ uh, double* __restrict__ Rh,
                     const double* __restrict__ h, const double2* __restrict__ w, const double* __restrict__ part,
                     int npart, double Cvel, double Crv, double* __restrict__ eps) {
   __shared__ double red[9];
   double A = 1.0;
-  if (variant == CFEM_EPS_LINEAR_SIMPLE) A = absolute_term(part, npart, n, red);
+  if (variant == CFEM_EPS_LINEAR_SIMPLE) A = absolute_term(part, npart, n_global, red);
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
     double b;
     if (FLUX == CFEM_FLUX_ADVECTION) {
@@ -193,39 +148,51 @@ k_epsilon_pointwise(int64_t n, int variant, const double* __restrict__ uh, doubl
   }
 }
 
+// all-reduce the sum / min / max partials over the ranks; returns the partial count to use
+static int stats_allreduce(cfem_ctx* c, int gv) {
+  double* sl[3] = {c->partials + P_SUM * kMaxPartials, c->partials + P_MIN * kMaxPartials, c->partials + P_MAX * kMaxPartials};
+  const int op[3] = {0, 1, 2};
+  return allreduce_partials(c, 3, sl, op, gv);
+}
+
 void launch_stats(cfem_ctx* c, const double* v) {
-  k_stats<-1><<<vec_grid(c, c->dm.nn), kBlock, 0, c->stream>>>(c->dm.nn, v, nullptr, c->partials); LAUNCHED(c);
+  const int gv = vec_grid(c, c->dm.nn);
+  k_stats<-1><<<gv, kBlock, 0, c->stream>>>(c->dm.no, c->dm.nn, v, nullptr, c->partials); LAUNCHED(c);
+  stats_allreduce(c, gv);
 }
 
 void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv, const double* uh,
                     const double* u_n, double* Rh, const double* h, const double2* w, double* eps) {
   ProfScope ps(c, PROF_RV);
-  const int64_t n = c->dm.nn;
-  const int gv = vec_grid(c, n);
+  const int64_t n = c->dm.no, nl = c->dm.nn, ng = c->dm.nn_global;
+  const int gv = vec_grid(c, nl);
+  int np = gv;
   if (!h) CFEM_THROW(-1, "rv_epsilon: nodal mesh size h is required");
   if (variant == CFEM_EPS_NONLINEAR || variant == CFEM_EPS_LINEAR) {
     if (!uh || !u_n || !Rh) CFEM_THROW(-1, "rv_epsilon: uh, u_n and Rh are required");
     double* beta = c->wk[9];
     if (variant == CFEM_EPS_LINEAR) {
       if (!w) CFEM_THROW(-1, "rv_epsilon(linear): velocity field w is required");
-      k_stats<-1><<<gv, kBlock, 0, c->stream>>>(n, uh, nullptr, c->partials);
+      k_stats<-1><<<gv, kBlock, 0, c->stream>>>(n, nl, uh, nullptr, c->partials);
     } else if (flux == CFEM_FLUX_BURGERS) {
-      k_stats<CFEM_FLUX_BURGERS><<<gv, kBlock, 0, c->stream>>>(n, uh, beta, c->partials);
+      k_stats<CFEM_FLUX_BURGERS><<<gv, kBlock, 0, c->stream>>>(n, nl, uh, beta, c->partials);
     } else if (flux == CFEM_FLUX_KPP) {
-      k_stats<CFEM_FLUX_KPP><<<gv, kBlock, 0, c->stream>>>(n, uh, beta, c->partials);
+      k_stats<CFEM_FLUX_KPP><<<gv, kBlock, 0, c->stream>>>(n, nl, uh, beta, c->partials);
     } else {
       CFEM_THROW(-1, "rv_epsilon(nonlinear): flux must be BURGERS or KPP");
     }
     LAUNCHED(c);
+    np = stats_allreduce(c, gv);
     int64_t g = (int64_t)c->sm_count * 4;
     if (g > c->dm.ntiles) g = c->dm.ntiles;
     if (variant == CFEM_EPS_LINEAR)
-      k_epsilon_stream<true><<<(int)g, kTileNodes, 0, c->stream>>>(c->dm.ntiles, n, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
-                                                                 u_n, Rh, nullptr, w, h, c->partials, gv, Cvel, Crv, eps);
+      k_epsilon_stream<true><<<(int)g, kTileNodes, 0, c->stream>>>(c->dm.ntiles, ng, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
+                                                                 u_n, Rh, nullptr, w, h, c->partials, np, Cvel, Crv, eps);
     else
-      k_epsilon_stream<false><<<(int)g, kTileNodes, 0, c->stream>>>(c->dm.ntiles, n, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
-                                                                  u_n, Rh, beta, w, h, c->partials, gv, Cvel, Crv, eps);
+      k_epsilon_stream<false><<<(int)g, kTileNodes, 0, c->stream>>>(c->dm.ntiles, ng, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
+                                                                  u_n, Rh, beta, w, h, c->partials, np, Cvel, Crv, eps);
     LAUNCHED(c);
+    halo_exchange(c, eps);
     return;
   }
   if (variant == CFEM_EPS_POINTWISE || variant == CFEM_EPS_FIRST_ORDER || variant == CFEM_EPS_LINEAR_SIMPLE) {
@@ -233,17 +200,18 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
     if (variant == CFEM_EPS_LINEAR_SIMPLE) {
       if (!u_n) CFEM_THROW(-1, "rv_epsilon(linear_simple): u_n is required");
       flux = CFEM_FLUX_ADVECTION;
-      k_stats<-1><<<gv, kBlock, 0, c->stream>>>(n, u_n, nullptr, c->partials); LAUNCHED(c);
+      k_stats<-1><<<gv, kBlock, 0, c->stream>>>(n, nl, u_n, nullptr, c->partials); LAUNCHED(c);
+      np = stats_allreduce(c, gv);
     }
     if (flux == CFEM_FLUX_ADVECTION) {
       if (!w) CFEM_THROW(-1, "rv_epsilon: velocity field w is required");
-      k_epsilon_pointwise<CFEM_FLUX_ADVECTION><<<gv, kBlock, 0, c->stream>>>(n, variant, uh, Rh, h, w, c->partials, gv, Cvel, Crv, eps);
+      k_epsilon_pointwise<CFEM_FLUX_ADVECTION><<<gv, kBlock, 0, c->stream>>>(nl, ng, variant, uh, Rh, h, w, c->partials, np, Cvel, Crv, eps);
     } else if (flux == CFEM_FLUX_BURGERS) {
       if (!uh) CFEM_THROW(-1, "rv_epsilon: uh is required");
-      k_epsilon_pointwise<CFEM_FLUX_BURGERS><<<gv, kBlock, 0, c->stream>>>(n, variant, uh, Rh, h, w, c->partials, gv, Cvel, Crv, eps);
+      k_epsilon_pointwise<CFEM_FLUX_BURGERS><<<gv, kBlock, 0, c->stream>>>(nl, ng, variant, uh, Rh, h, w, c->partials, np, Cvel, Crv, eps);
     } else if (flux == CFEM_FLUX_KPP) {
       if (!uh) CFEM_THROW(-1, "rv_epsilon: uh is required");
-      k_epsilon_pointwise<CFEM_FLUX_KPP><<<gv, kBlock, 0, c->stream>>>(n, variant, uh, Rh, h, w, c->partials, gv, Cvel, Crv, eps);
+      k_epsilon_pointwise<CFEM_FLUX_KPP><<<gv, kBlock, 0, c->stream>>>(nl, ng, variant, uh, Rh, h, w, c->partials, np, Cvel, Crv, eps);
     } else {
       CFEM_THROW(-1, "rv_epsilon: unknown flux");
     }
@@ -289,13 +257,14 @@ __device__ double burgers_exact(double X, double Y, double t) {
   return u;
 }
 
-__global__ void k_bc_values(int64_t nbc, const int32_t* __restrict__ bc_nodes, int kind, double value, double t,
-                            const double* __restrict__ user, const double2* __restrict__ xy, double* __restrict__ g) {
+__global__ void k_bc_values(int64_t nbc, const int32_t* __restrict__ bc_nodes, const int32_t* __restrict__ bc_pos,
+                            int kind, double value, double t, const double* __restrict__ user,
+                            const double2* __restrict__ xy, double* __restrict__ g) {
   for (int64_t j = blockIdx.x * (int64_t)kBlock + threadIdx.x; j < nbc; j += (int64_t)gridDim.x * kBlock) {
     const int node = bc_nodes[j];
     double v;
     if (kind == CFEM_BC_CONSTANT) v = value;
-    else if (kind == CFEM_BC_USER) v = user[j];
+    else if (kind == CFEM_BC_USER) v = user[bc_pos[j]];
     else { const double2 p = xy[node]; v = burgers_exact(p.x, p.y, t); }
     g[node] = v;
   }
@@ -305,7 +274,7 @@ void launch_bc_values(cfem_ctx* c, int kind, double value, double t, const doubl
   if (c->nbc == 0) return;
   if (kind == CFEM_BC_USER && !user_vals) CFEM_THROW(-1, "CFEM_BC_USER needs bc_values");
   ProfScope ps(c, PROF_MISC);
-  k_bc_values<<<vec_grid(c, c->nbc), kBlock, 0, c->stream>>>(c->nbc, c->d_bc_nodes, kind, value, t, user_vals, c->dm.xy, g);
+  k_bc_values<<<vec_grid(c, c->nbc), kBlock, 0, c->stream>>>(c->nbc, c->d_bc_nodes, c->d_bc_pos, kind, value, t, user_vals, c->dm.xy, g);
   LAUNCHED(c);
 }
 

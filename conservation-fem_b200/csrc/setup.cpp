@@ -1,7 +1,9 @@
 // Host-side, once-per-mesh analysis: Hilbert ordering, vertex->cell adjacency,
 // P1 CSR pattern (== node patches, reference Code/Utils/SI.py:12-28), boundary
-// dofs (reference Code/KPP/KPP_exact.py:85-89), and the assembly tiles with
-// their packed (node, cell) codes.  Everything is O(N) apart from one sort.
+// dofs (reference Code/KPP/KPP_exact.py:85-89), the partition of the Hilbert
+// curve into one contiguous range of nodes per rank with its ghost layer and
+// halo-exchange lists, and the assembly tiles with their packed (node, cell)
+// codes.  Everything is O(N) apart from one sort.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -38,20 +40,34 @@ static void sort_pairs(It b, It e) {
 #endif
 }
 
-void analyse_mesh(HostMesh& hm, int64_t nn, int64_t nc, const double* x, int xdim,
-                  const void* cells_in, int idx_bytes, int order) {
+// Whole-mesh relations in global internal numbering.
+struct GlobalMesh {
+  int64_t nn = 0, nc = 0;
+  std::vector<int32_t> n2u, u2n;
+  std::vector<double> xy;
+  std::vector<int32_t> cells;    // 3*nc, sorted by smallest vertex
+  std::vector<int32_t> v2c_ptr;  // nn+1
+  std::vector<int32_t> v2c;      // 3*nc  cell of each (vertex, incident cell) pair, ascending
+  std::vector<uint8_t> v2k;      // 3*nc  local vertex number in that cell
+  std::vector<int32_t> rowptr, colidx;
+  std::vector<uint8_t> is_bnd;
+  int max_row = 0;
+};
+
+static void global_analysis(GlobalMesh& g, int64_t nn, int64_t nc, const double* x, int xdim,
+                            const void* cells_in, int idx_bytes, int order) {
   if (nn <= 0 || nc <= 0) CFEM_THROW(-1, "empty mesh");
   if (nn >= (int64_t)1 << 31 || 3 * nc >= (int64_t)1 << 31) CFEM_THROW(-1, "mesh too large for int32 indices");
   if (xdim != 2 && xdim != 3) CFEM_THROW(-1, "xdim must be 2 or 3");
   if (idx_bytes != 4 && idx_bytes != 8) CFEM_THROW(-1, "cell_index_bytes must be 4 or 8");
-  hm.nn = nn;
-  hm.nc = nc;
+  g.nn = nn;
+  g.nc = nc;
 
   // ---- 1. node ordering ----------------------------------------------------
-  hm.n2u.resize(nn);
-  hm.u2n.resize(nn);
+  g.n2u.resize(nn);
+  g.u2n.resize(nn);
   if (order == CFEM_ORDER_NATURAL) {
-    std::iota(hm.n2u.begin(), hm.n2u.end(), 0);
+    std::iota(g.n2u.begin(), g.n2u.end(), 0);
   } else {
     double xmin = x[0], xmax = x[0], ymin = x[1], ymax = x[1];
     for (int64_t i = 0; i < nn; ++i) {
@@ -72,134 +88,267 @@ void analyse_mesh(HostMesh& hm, int64_t nn, int64_t nc, const double* x, int xdi
     }
     sort_pairs(keys.begin(), keys.end());
 #pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < nn; ++i) hm.n2u[i] = keys[i].second;
+    for (int64_t i = 0; i < nn; ++i) g.n2u[i] = keys[i].second;
   }
 #pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < nn; ++i) hm.u2n[hm.n2u[i]] = (int32_t)i;
-  hm.xy.resize(2 * nn);
+  for (int64_t i = 0; i < nn; ++i) g.u2n[g.n2u[i]] = (int32_t)i;
+  g.xy.resize(2 * nn);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < nn; ++i) {
-    const int64_t u = hm.n2u[i];
-    hm.xy[2 * i] = x[u * xdim];
-    hm.xy[2 * i + 1] = x[u * xdim + 1];
+    const int64_t u = g.n2u[i];
+    g.xy[2 * i] = x[u * xdim];
+    g.xy[2 * i + 1] = x[u * xdim + 1];
   }
 
   // ---- 2. cells -> internal ids, ordered by their smallest vertex -----------
   std::vector<int32_t> ctmp(3 * nc);
   {
-    bool bad = false;
-#pragma omp parallel for schedule(static) reduction(|| : bad)
+    bool range_bad = false, rep_bad = false;
+#pragma omp parallel for schedule(static) reduction(|| : range_bad) reduction(|| : rep_bad)
     for (int64_t c = 0; c < nc; ++c) {
       for (int k = 0; k < 3; ++k) {
         int64_t v = idx_bytes == 4 ? (int64_t)((const int32_t*)cells_in)[3 * c + k]
                                    : (int64_t)((const int64_t*)cells_in)[3 * c + k];
-        if (v < 0 || v >= nn) { bad = true; v = 0; }
-        ctmp[3 * c + k] = hm.u2n[v];
+        if (v < 0 || v >= nn) { range_bad = true; v = 0; }
+        ctmp[3 * c + k] = g.u2n[v];
       }
       if (ctmp[3 * c] == ctmp[3 * c + 1] || ctmp[3 * c] == ctmp[3 * c + 2] || ctmp[3 * c + 1] == ctmp[3 * c + 2])
-        bad = true;
+        rep_bad = true;
     }
-    if (bad) CFEM_THROW(-1, "cell connectivity has an out-of-range or repeated vertex");
+    if (range_bad) CFEM_THROW(-1, "cell connectivity has an out-of-range vertex");
+    if (rep_bad) CFEM_THROW(-1, "cell connectivity has a repeated vertex");
   }
-  hm.cells.resize(3 * nc);
+  g.cells.resize(3 * nc);
   {
-    // counting sort by min vertex (stable -> deterministic)
-    std::vector<int32_t> cnt(nn + 1, 0);
+    std::vector<int32_t> cnt(nn + 1, 0);  // counting sort by min vertex (stable -> deterministic)
     for (int64_t c = 0; c < nc; ++c)
       cnt[std::min(ctmp[3 * c], std::min(ctmp[3 * c + 1], ctmp[3 * c + 2])) + 1]++;
     for (int64_t i = 0; i < nn; ++i) cnt[i + 1] += cnt[i];
     for (int64_t c = 0; c < nc; ++c) {
       const int32_t m = std::min(ctmp[3 * c], std::min(ctmp[3 * c + 1], ctmp[3 * c + 2]));
       const int64_t p = cnt[m]++;
-      hm.cells[3 * p] = ctmp[3 * c];
-      hm.cells[3 * p + 1] = ctmp[3 * c + 1];
-      hm.cells[3 * p + 2] = ctmp[3 * c + 2];
+      g.cells[3 * p] = ctmp[3 * c];
+      g.cells[3 * p + 1] = ctmp[3 * c + 1];
+      g.cells[3 * p + 2] = ctmp[3 * c + 2];
     }
   }
-  ctmp.clear();
-  ctmp.shrink_to_fit();
+  std::vector<int32_t>().swap(ctmp);
 
   // ---- 3. vertex -> (cell, k), cells ascending ------------------------------
-  hm.v2c_ptr.assign(nn + 1, 0);
-  for (int64_t e = 0; e < 3 * nc; ++e) hm.v2c_ptr[hm.cells[e] + 1]++;
+  g.v2c_ptr.assign(nn + 1, 0);
+  for (int64_t e = 0; e < 3 * nc; ++e) g.v2c_ptr[g.cells[e] + 1]++;
   for (int64_t i = 0; i < nn; ++i) {
-    if (hm.v2c_ptr[i + 1] == 0) CFEM_THROW(-1, "mesh has a node that belongs to no cell (node " + std::to_string(hm.n2u[i]) + ")");
-    hm.v2c_ptr[i + 1] += hm.v2c_ptr[i];
+    if (g.v2c_ptr[i + 1] == 0)
+      CFEM_THROW(-1, "mesh has a node that belongs to no cell (node " + std::to_string(g.n2u[i]) + ")");
+    g.v2c_ptr[i + 1] += g.v2c_ptr[i];
   }
-  std::vector<int32_t> v2c(3 * nc);  // entry = 4*cell... stored as cell*4+k would overflow; keep two arrays
-  std::vector<uint8_t> v2k(3 * nc);
+  g.v2c.resize(3 * nc);
+  g.v2k.resize(3 * nc);
   {
-    std::vector<int32_t> fill(hm.v2c_ptr.begin(), hm.v2c_ptr.end() - 1);
+    std::vector<int32_t> fill(g.v2c_ptr.begin(), g.v2c_ptr.end() - 1);
     for (int64_t c = 0; c < nc; ++c)
       for (int k = 0; k < 3; ++k) {
-        const int64_t p = fill[hm.cells[3 * c + k]]++;
-        v2c[p] = (int32_t)c;
-        v2k[p] = (uint8_t)k;
+        const int64_t p = fill[g.cells[3 * c + k]]++;
+        g.v2c[p] = (int32_t)c;
+        g.v2k[p] = (uint8_t)k;
       }
   }
 
   // ---- 4. CSR pattern (sorted rows) + boundary flags ------------------------
-  hm.rowptr.assign(nn + 1, 0);
+  g.rowptr.assign(nn + 1, 0);
   int max_row = 0;
   bool row_overflow = false;
 #pragma omp parallel for schedule(static) reduction(max : max_row) reduction(|| : row_overflow)
   for (int64_t i = 0; i < nn; ++i) {
     int32_t buf[3 * 64];
-    const int deg = hm.v2c_ptr[i + 1] - hm.v2c_ptr[i];
+    const int deg = g.v2c_ptr[i + 1] - g.v2c_ptr[i];
     if (deg > 64) { row_overflow = true; continue; }
     int m = 0;
-    for (int e = hm.v2c_ptr[i]; e < hm.v2c_ptr[i + 1]; ++e)
-      for (int k = 0; k < 3; ++k) buf[m++] = hm.cells[3 * (int64_t)v2c[e] + k];
+    for (int e = g.v2c_ptr[i]; e < g.v2c_ptr[i + 1]; ++e)
+      for (int k = 0; k < 3; ++k) buf[m++] = g.cells[3 * (int64_t)g.v2c[e] + k];
     std::sort(buf, buf + m);
     const int len = (int)(std::unique(buf, buf + m) - buf);
-    hm.rowptr[i + 1] = len;
+    g.rowptr[i + 1] = len;
     max_row = std::max(max_row, len);
   }
   if (row_overflow || max_row > kMaxRow)
     CFEM_THROW(-1, "a node has more than " + std::to_string(kMaxRow - 1) + " neighbours; unsupported mesh");
-  for (int64_t i = 0; i < nn; ++i) hm.rowptr[i + 1] += hm.rowptr[i];
-  hm.nnz = hm.rowptr[nn];
-  hm.max_row = max_row;
-  hm.colidx.resize(hm.nnz);
-  hm.is_bnd.assign(nn, 0);
-  std::vector<uint8_t> bnd_edge_flag(hm.nnz, 0);
+  for (int64_t i = 0; i < nn; ++i) g.rowptr[i + 1] += g.rowptr[i];
+  g.max_row = max_row;
+  g.colidx.resize(g.rowptr[nn]);
+  g.is_bnd.assign(nn, 0);
+  std::vector<uint8_t> bnd_edge_flag(g.rowptr[nn], 0);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < nn; ++i) {
     int32_t buf[3 * 64];
     int m = 0;
-    for (int e = hm.v2c_ptr[i]; e < hm.v2c_ptr[i + 1]; ++e)
-      for (int k = 0; k < 3; ++k) buf[m++] = hm.cells[3 * (int64_t)v2c[e] + k];
+    for (int e = g.v2c_ptr[i]; e < g.v2c_ptr[i + 1]; ++e)
+      for (int k = 0; k < 3; ++k) buf[m++] = g.cells[3 * (int64_t)g.v2c[e] + k];
     std::sort(buf, buf + m);
-    // run lengths: neighbour j shares (count) cells with i; 1 => boundary edge
-    int32_t* row = &hm.colidx[hm.rowptr[i]];
+    // run lengths: neighbour j shares (count) cells with i; exactly 1 => boundary edge
+    int32_t* row = &g.colidx[g.rowptr[i]];
     int len = 0;
     for (int a = 0; a < m;) {
       int b = a;
       while (b < m && buf[b] == buf[a]) ++b;
       row[len] = buf[a];
-      if (buf[a] != (int32_t)i && (b - a) == 1) bnd_edge_flag[hm.rowptr[i] + len] = 1;
+      if (buf[a] != (int32_t)i && (b - a) == 1) bnd_edge_flag[g.rowptr[i] + len] = 1;
       ++len;
       a = b;
     }
   }
   for (int64_t i = 0; i < nn; ++i)
-    for (int p = hm.rowptr[i]; p < hm.rowptr[i + 1]; ++p)
-      if (bnd_edge_flag[p]) { hm.is_bnd[i] = 1; hm.is_bnd[hm.colidx[p]] = 1; }
-  bnd_edge_flag.clear();
+    for (int p = g.rowptr[i]; p < g.rowptr[i + 1]; ++p)
+      if (bnd_edge_flag[p]) { g.is_bnd[i] = 1; g.is_bnd[g.colidx[p]] = 1; }
+}
+
+// Restrict the global relations to rank's contiguous range of the curve plus one ghost layer.
+static void build_local(const GlobalMesh& g, int rank, int world, HostMesh& hm, std::vector<int32_t>& lv2c,
+                        std::vector<uint8_t>& lv2k) {
+  const int64_t nn = g.nn;
+  hm.rank = rank;
+  hm.world = world;
+  hm.nn_global = nn;
+  hm.part_off.resize(world + 1);
+  for (int r = 0; r <= world; ++r) hm.part_off[r] = (int64_t)((__int128)nn * r / world);
+  const int64_t lo = hm.part_off[rank], hi = hm.part_off[rank + 1];
+  const int64_t no = hi - lo;
+  if (no <= 0) CFEM_THROW(-1, "a rank owns no node: mesh too small for this many ranks");
+  hm.n_owned = no;
+  hm.max_row = g.max_row;
+  auto owner_of = [&](int32_t node) {
+    return (int)(std::upper_bound(hm.part_off.begin(), hm.part_off.end(), (int64_t)node) - hm.part_off.begin()) - 1;
+  };
+
+  // local cells: every cell touching an owned node, ascending global order
+  std::vector<int32_t> lcells;
+  if (world == 1) {
+    lcells.resize(g.nc);
+    std::iota(lcells.begin(), lcells.end(), 0);
+  } else {
+    std::vector<uint8_t> mark(g.nc, 0);
+    for (int64_t e = g.v2c_ptr[lo]; e < g.v2c_ptr[hi]; ++e) mark[g.v2c[e]] = 1;
+    for (int64_t c = 0; c < g.nc; ++c)
+      if (mark[c]) lcells.push_back((int32_t)c);
+  }
+  const int64_t nc = (int64_t)lcells.size();
+  hm.nc = nc;
+
+  // ghosts: vertices of local cells outside [lo, hi), ascending global id (=> grouped by owner)
+  std::vector<int32_t> ghosts;
+  if (world > 1) {
+    for (int64_t c = 0; c < nc; ++c)
+      for (int k = 0; k < 3; ++k) {
+        const int32_t v = g.cells[3 * (int64_t)lcells[c] + k];
+        if (v < lo || v >= hi) ghosts.push_back(v);
+      }
+    std::sort(ghosts.begin(), ghosts.end());
+    ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
+  }
+  const int64_t ng = (int64_t)ghosts.size();
+  hm.ghost_global = ghosts;
+  const int64_t nl = no + ng;
+  hm.nn = nl;
+  auto to_local = [&](int32_t v) -> int32_t {
+    if (v >= lo && v < hi) return (int32_t)(v - lo);
+    return (int32_t)(no + (std::lower_bound(ghosts.begin(), ghosts.end(), v) - ghosts.begin()));
+  };
+  auto to_global = [&](int64_t l) -> int32_t { return l < no ? (int32_t)(lo + l) : ghosts[l - no]; };
+
+  hm.n2u.resize(nl);
+  hm.xy.resize(2 * nl);
+  hm.is_bnd.resize(nl);
+#pragma omp parallel for schedule(static)
+  for (int64_t l = 0; l < nl; ++l) {
+    const int32_t v = to_global(l);
+    hm.n2u[l] = g.n2u[v];
+    hm.xy[2 * l] = g.xy[2 * (int64_t)v];
+    hm.xy[2 * l + 1] = g.xy[2 * (int64_t)v + 1];
+    hm.is_bnd[l] = g.is_bnd[v];
+  }
+  hm.u2n = g.u2n;  // user -> GLOBAL internal id (only meaningful together with part_off)
+  hm.cells.resize(3 * nc);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < nc; ++c)
+    for (int k = 0; k < 3; ++k) hm.cells[3 * c + k] = to_local(g.cells[3 * (int64_t)lcells[c] + k]);
+
+  // owned rows, columns kept in ascending GLOBAL order (so every rank count sums a row in the same order)
+  hm.rowptr.resize(no + 1);
+  for (int64_t i = 0; i <= no; ++i) hm.rowptr[i] = g.rowptr[lo + i] - g.rowptr[lo];
+  hm.nnz = hm.rowptr[no];
+  hm.colidx.resize(hm.nnz);
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < hm.nnz; ++p) hm.colidx[p] = to_local(g.colidx[g.rowptr[lo] + p]);
+
+  // vertex -> cell adjacency of owned nodes, local cell ids
+  hm.v2c_ptr.resize(no + 1);
+  for (int64_t i = 0; i <= no; ++i) hm.v2c_ptr[i] = g.v2c_ptr[lo + i] - g.v2c_ptr[lo];
+  const int64_t ne = hm.v2c_ptr[no];
+  lv2c.resize(ne);
+  lv2k.resize(ne);
+  if (world == 1) {
+    lv2c = g.v2c;
+    lv2k = g.v2k;
+  } else {
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < ne; ++e) {
+      const int32_t gc = g.v2c[g.v2c_ptr[lo] + e];
+      lv2c[e] = (int32_t)(std::lower_bound(lcells.begin(), lcells.end(), gc) - lcells.begin());
+      lv2k[e] = g.v2k[g.v2c_ptr[lo] + e];
+    }
+  }
+
+  // boundary dofs in caller numbering: global list (every rank reports the same set)
   hm.bnd_user_sorted.clear();
   for (int64_t i = 0; i < nn; ++i)
-    if (hm.is_bnd[i]) hm.bnd_user_sorted.push_back(hm.n2u[i]);
+    if (g.is_bnd[i]) hm.bnd_user_sorted.push_back(g.n2u[i]);
   std::sort(hm.bnd_user_sorted.begin(), hm.bnd_user_sorted.end());
 
-  // ---- 5. tiles + packed codes -----------------------------------------------
-  hm.v2c_code.resize(3 * nc);
-  hm.tile_node.clear();
-  hm.tile_cellptr.clear();
+  // halo exchange lists
+  hm.peer_rank.clear();
+  hm.send_ptr.assign(1, 0);
+  hm.send_idx.clear();
+  hm.recv_off.clear();
+  hm.recv_cnt.clear();
+  if (world > 1) {
+    std::vector<std::vector<int32_t>> send(world);
+    for (int64_t c = 0; c < nc; ++c) {
+      int own[3];
+      int32_t v[3];
+      for (int k = 0; k < 3; ++k) { v[k] = g.cells[3 * (int64_t)lcells[c] + k]; own[k] = owner_of(v[k]); }
+      for (int a = 0; a < 3; ++a)
+        if (own[a] == rank)
+          for (int b = 0; b < 3; ++b)
+            if (own[b] != rank) send[own[b]].push_back(v[a]);
+    }
+    std::vector<int64_t> rcnt(world, 0), roff(world, 0);
+    for (int64_t k = 0; k < ng; ++k) rcnt[owner_of(ghosts[k])]++;
+    int64_t acc = 0;
+    for (int r = 0; r < world; ++r) { roff[r] = acc; acc += rcnt[r]; }
+    for (int r = 0; r < world; ++r) {
+      auto& s = send[r];
+      std::sort(s.begin(), s.end());
+      s.erase(std::unique(s.begin(), s.end()), s.end());
+      if (s.empty() && rcnt[r] == 0) continue;
+      hm.peer_rank.push_back(r);
+      for (int32_t v : s) hm.send_idx.push_back((int32_t)(v - lo));
+      hm.send_ptr.push_back((int32_t)hm.send_idx.size());
+      hm.recv_off.push_back((int32_t)(no + roff[r]));
+      hm.recv_cnt.push_back((int32_t)rcnt[r]);
+    }
+  }
+}
+
+// Tiles over the owned nodes + packed codes.
+static void build_tiles(HostMesh& hm, const std::vector<int32_t>& v2c, const std::vector<uint8_t>& v2k) {
+  const int64_t no = hm.n_owned, nc = hm.nc;
+  hm.v2c_code.resize(v2c.size());
+  hm.tile_node.assign(1, 0);
+  hm.tile_cellptr.assign(1, 0);
   hm.tile_cells.clear();
-  hm.tile_node.push_back(0);
-  hm.tile_cellptr.push_back(0);
+  hm.max_tile_cells = hm.max_tile_nnz = 0;
   std::vector<int32_t> stamp(nc, -1), loc(nc, 0);
-  std::vector<int32_t> cur;  // cells of the open tile
+  std::vector<int32_t> cur;
   cur.reserve(kTileCellCap);
   int64_t tile_begin = 0;
   int tile_nnz = 0, tile_id = 0;
@@ -214,7 +363,8 @@ void analyse_mesh(HostMesh& hm, int64_t nn, int64_t nc, const double* x, int xdi
         uint32_t code = (uint32_t)loc[c] | ((uint32_t)v2k[e] << kCodeCellBits);
         for (int j = 0; j < 3; ++j) {
           const int32_t col = hm.cells[3 * c + j];
-          const int pos = (int)(std::lower_bound(row, row + len, col) - row);
+          int pos = 0;
+          while (pos < len && row[pos] != col) ++pos;  // rows are short; order may not be sorted locally
           code |= (uint32_t)pos << (kCodeCellBits + 2 + 5 * j);
         }
         hm.v2c_code[e] = code;
@@ -230,7 +380,7 @@ void analyse_mesh(HostMesh& hm, int64_t nn, int64_t nc, const double* x, int xdi
     tile_nnz = 0;
     ++tile_id;
   };
-  for (int64_t i = 0; i < nn; ++i) {
+  for (int64_t i = 0; i < no; ++i) {
     const int len = hm.rowptr[i + 1] - hm.rowptr[i];
     int fresh = 0;
     for (int e = hm.v2c_ptr[i]; e < hm.v2c_ptr[i + 1]; ++e)
@@ -243,7 +393,29 @@ void analyse_mesh(HostMesh& hm, int64_t nn, int64_t nc, const double* x, int xdi
     tile_nnz += len;
     if ((int)cur.size() > kTileCellCap) CFEM_THROW(-1, "node valence exceeds tile capacity");
   }
-  close_tile(nn);
+  close_tile(no);
+}
+
+int32_t user_to_local(const HostMesh& hm, int64_t user_dof) {
+  if (user_dof < 0 || user_dof >= hm.nn_global) return -1;
+  const int64_t g = hm.u2n[user_dof];
+  const int64_t lo = hm.part_off[hm.rank], hi = hm.part_off[hm.rank + 1];
+  if (g >= lo && g < hi) return (int32_t)(g - lo);
+  auto it = std::lower_bound(hm.ghost_global.begin(), hm.ghost_global.end(), (int32_t)g);
+  if (it != hm.ghost_global.end() && *it == (int32_t)g) return (int32_t)(hm.n_owned + (it - hm.ghost_global.begin()));
+  return -1;
+}
+
+void analyse_mesh(HostMesh& hm, int64_t nn, int64_t nc, const double* x, int xdim, const void* cells,
+                  int idx_bytes, int order, int rank, int world) {
+  if (world < 1 || rank < 0 || rank >= world) CFEM_THROW(-1, "bad rank / world size");
+  GlobalMesh g;
+  global_analysis(g, nn, nc, x, xdim, cells, idx_bytes, order);
+  std::vector<int32_t> lv2c;
+  std::vector<uint8_t> lv2k;
+  build_local(g, rank, world, hm, lv2c, lv2k);
+  g = GlobalMesh();  // release the global relations before tiling
+  build_tiles(hm, lv2c, lv2k);
 }
 
 }  // namespace cfem

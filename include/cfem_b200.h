@@ -70,6 +70,22 @@ int cfem_device_count(void);
 int cfem_create(cfem_ctx** out, int device, int64_t n_nodes, int64_t n_cells,
                 const double* x, int xdim, const void* cells, int cell_index_bytes,
                 int order);
+/* ---- multi-GPU: one process per GPU, one context per process ----
+ * Every rank passes the SAME global mesh; the library orders it along the Hilbert curve,
+ * gives rank r the r-th contiguous range of nodes (its rows) plus one layer of ghost nodes and
+ * all cells touching an owned node, so assembly needs no reverse exchange.  Ghost values are
+ * refreshed by grouped ncclSend/ncclRecv before every SpMV / assembly, Krylov dot products and
+ * the RV normalisation (sum/min/max) by ncclAllReduce.  nccl_id128: the 128-byte ncclUniqueId
+ * made by cfem_nccl_unique_id on rank 0 and broadcast by the caller (torch.distributed).
+ * Field arguments of every other entry point stay GLOBAL-sized arrays in caller numbering;
+ * outputs are written at the dofs this rank owns.  Calls are collective. */
+int cfem_nccl_unique_id(void* out128);
+int cfem_create_distributed(cfem_ctx** out, int device, int rank, int world, const void* nccl_id128,
+                            int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
+                            const void* cells, int cell_index_bytes, int order);
+int64_t cfem_num_owned(const cfem_ctx* ctx);
+int64_t cfem_num_ghosts(const cfem_ctx* ctx);
+int cfem_comm_stats(const cfem_ctx* ctx, int64_t* halo_exchanges, int64_t* allreduces, int64_t* halo_doubles_sent);
 void cfem_destroy(cfem_ctx* ctx);
 int cfem_synchronize(cfem_ctx* ctx);
 
@@ -206,7 +222,8 @@ enum { CFEM_KERNEL_SPMV = 0, CFEM_KERNEL_ASM_RESIDUAL = 1, CFEM_KERNEL_ASM_JACOB
  * the device time and launch count per category:
  *   0 SpMV  1 vector assembly  2 matrix assembly  3 Krylov vector kernels
  *   4 RV (stats + epsilon)     5 misc (gather/fill/axpy/bc)
- *   6 fused Chebyshev mass-solve iteration (SpMV + update)              (arrays of 8) */
+ *   6 fused Chebyshev mass-solve iteration (SpMV + update)
+ *   7 communication (halo pack + NCCL send/recv, all-reduce)            (arrays of 8) */
 int cfem_profile_begin(cfem_ctx* ctx, int max_launches);
 int cfem_profile_end(cfem_ctx* ctx, double* ms_per_category, int64_t* launches_per_category);
 int cfem_time_kernel(cfem_ctx* ctx, int kernel, int flux, int reps, double* ms_per_launch,
@@ -219,9 +236,17 @@ int cfem_time_kernel(cfem_ctx* ctx, int kernel, int flux, int reps, double* ms_p
 typedef struct cfem_host_mesh cfem_host_mesh;
 enum { CFEM_HM_N2U = 0, CFEM_HM_CELLS = 1, CFEM_HM_ROWPTR = 2, CFEM_HM_COLIDX = 3, CFEM_HM_V2C_PTR = 4,
        CFEM_HM_V2C_CODE = 5, CFEM_HM_TILE_NODE = 6, CFEM_HM_TILE_CELLPTR = 7, CFEM_HM_TILE_CELLS = 8,
-       CFEM_HM_IS_BND = 9 /* uint8 */, CFEM_HM_BND_USER = 10 };
+       CFEM_HM_IS_BND = 9 /* uint8 */, CFEM_HM_BND_USER = 10,
+       /* partition (cfem_host_analyse_part): peers and halo lists of this rank */
+       CFEM_HM_PEER_RANK = 11, CFEM_HM_SEND_PTR = 12, CFEM_HM_SEND_IDX = 13, CFEM_HM_RECV_OFF = 14,
+       CFEM_HM_RECV_CNT = 15 };
 int cfem_host_analyse(cfem_host_mesh** out, int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
                       const void* cells, int cell_index_bytes, int order);
+/* same, restricted to rank's part of a world-way partition (what cfem_create_distributed builds) */
+int cfem_host_analyse_part(cfem_host_mesh** out, int rank, int world, int64_t n_nodes, int64_t n_cells,
+                           const double* x, int xdim, const void* cells, int cell_index_bytes, int order);
+/* what: 0 owned nodes, 1 local nodes (owned + ghosts), 2 global nodes, 3 local cells, 4 nnz of owned rows */
+int64_t cfem_host_info(const cfem_host_mesh* hm, int what);
 /* number of elements of array `what` (4-byte elements except CFEM_HM_IS_BND) */
 int64_t cfem_host_size(const cfem_host_mesh* hm, int what);
 int cfem_host_copy(const cfem_host_mesh* hm, int what, void* dst);

@@ -122,3 +122,19 @@ def test_kpp_4M_cells_unstructured_steps():
     assert np.array_equal(x[k1], x2[k2])
     assert rel(u[k1], uh2.x.array[k2]) < 1e-9
     ctx.close()
+
+
+def test_two_gpu_partition_parity():
+    """Domain-decomposed run (NCCL halo exchange + all-reduce) against the oracle; needs >= 2 GPUs."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run tests/dist_gpu_check.py under torchrun on a multi-GPU box)")
+    script = os.path.join(os.path.dirname(__file__), "dist_gpu_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
