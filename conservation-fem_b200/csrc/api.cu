@@ -16,16 +16,20 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 ProfScope::ProfScope(cfem_ctx* c_, int cat) : c(c_), active(false) {
   Profiler& p = c->prof;
-  if (!p.on || p.used + 2 > p.ev.size()) return;
+  if (!p.on) return;
+  if (p.depth++ > 0) return;  // nested scopes are charged to the outermost category
+  if (p.used + 2 > p.ev.size()) return;
   active = true;
-  p.cat[p.used / 2] = cat;
-  cudaEventRecord(p.ev[p.used], c->stream);
+  idx = p.used;
+  p.used += 2;
+  p.cat[idx / 2] = cat;
+  cudaEventRecord(p.ev[idx], c->stream);
 }
 ProfScope::~ProfScope() {
-  if (!active) return;
   Profiler& p = c->prof;
-  cudaEventRecord(p.ev[p.used + 1], c->stream);
-  p.used += 2;
+  if (p.on && p.depth > 0) --p.depth;
+  if (!active) return;
+  cudaEventRecord(p.ev[idx + 1], c->stream);
 }
 }  // namespace cfem
 
@@ -734,6 +738,7 @@ int cfem_profile_begin(cfem_ctx* c, int max_launches) {
   }
   p.cat.assign(p.ev.size() / 2, 0);
   p.used = 0;
+  p.depth = 0;
   p.on = true;
   API_END
 }

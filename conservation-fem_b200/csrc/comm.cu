@@ -8,6 +8,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <map>
+#include <string>
+
 #include "device_utils.cuh"
 #include "launch.h"
 
@@ -70,17 +73,22 @@ void comm_init(cfem_ctx* c, int rank, int world, const void* id128) {
   c->rank = rank;
   c->world = world;
   if (world == 1) return;
-  ncclUniqueId id;
-  memcpy(&id, id128, sizeof(id));
-  ncclComm_t comm;
-  NCCL_OK(nccl().CommInitRank(&comm, world, id, rank));
-  c->nccl_comm = comm;
+  // One communicator per unique id for the life of the process: contexts made with the same
+  // id (several meshes in one run) share it; an id can only be used for one ncclCommInitRank.
+  static std::map<std::string, ncclComm_t> cache;
+  const std::string key((const char*)id128, sizeof(ncclUniqueId));
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm;
+    NCCL_OK(nccl().CommInitRank(&comm, world, id, rank));
+    it = cache.emplace(key, comm).first;
+  }
+  c->nccl_comm = it->second;
 }
 
-void comm_destroy(cfem_ctx* c) {
-  if (c->nccl_comm) nccl().CommDestroy((ncclComm_t)c->nccl_comm);
-  c->nccl_comm = nullptr;
-}
+void comm_destroy(cfem_ctx* c) { c->nccl_comm = nullptr; }  // communicators are process-lifetime
 
 template <class T>
 __global__ void k_pack(const T* __restrict__ v, const int32_t* __restrict__ idx, T* __restrict__ out, int n) {

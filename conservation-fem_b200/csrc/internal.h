@@ -103,6 +103,7 @@ struct Profiler {
   std::vector<cudaEvent_t> ev;   // pairs
   std::vector<int> cat;
   size_t used = 0;               // events used
+  int depth = 0;                 // nesting depth of live scopes
 };
 
 }  // namespace cfem
@@ -111,7 +112,7 @@ struct cfem_ctx;
 namespace cfem {
 // RAII: brackets the launches issued inside its scope with two events when profiling is on.
 struct ProfScope {
-  cfem_ctx* c; bool active;
+  cfem_ctx* c; bool active; size_t idx = 0;
   ProfScope(cfem_ctx* c, int cat);
   ~ProfScope();
 };
