@@ -101,6 +101,9 @@ SIGNATURES = {
     "cfem_state_get": (_I, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(_D)]),
     "cfem_step_scalar": (_I, [_P, C.POINTER(StepParams), _I, _P, C.POINTER(StepStats)]),
     "cfem_step_advection": (_I, [_P, C.POINTER(StepParams), _I, _I, C.POINTER(StepStats)]),
+    "cfem_euler_state_set": (_I, [_P, _P, _P, _P, _P, _P, _P, _D]),
+    "cfem_euler_state_get": (_I, [_P, _P, _P, _P, C.POINTER(_D)]),
+    "cfem_step_euler": (_I, [_P, C.POINTER(StepParams), _I, C.POINTER(StepStats)]),
     "cfem_profile_begin": (_I, [_P, _I]),
     "cfem_profile_end": (_I, [_P, C.POINTER(_D), C.POINTER(_L)]),
     "cfem_time_kernel": (_I, [_P, _I, _I, _I, C.POINTER(_D), C.POINTER(_D)]),

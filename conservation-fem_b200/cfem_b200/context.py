@@ -233,6 +233,31 @@ class Context:
                                               C.byref(st)))
         return st.as_dict()
 
+    # -- (a-12) Euler system: (Nn,4) arrays
+    def euler_state_set(self, Uh=None, Un=None, Uold=None, Uoo=None, bc_state=None, h=None, t=0.0):
+        args = [None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(self.n, 4)
+                for a in (Uh, Un, Uold, Uoo, bc_state)]
+        hh = _field(h)
+        L.check(self._lib.cfem_euler_state_set(self._h, *[L.ptr(a) for a in args], L.ptr(hh), float(t)))
+
+    def euler_state_get(self, want=("Uh",)):
+        out = {}
+        Uh = np.zeros((self.n, 4)) if "Uh" in want else None
+        R = np.zeros((self.n, 4)) if "R" in want else None
+        eps = np.zeros(self.n) if "eps" in want else None
+        t = C.c_double(0.0)
+        L.check(self._lib.cfem_euler_state_get(self._h, L.ptr(Uh), L.ptr(R), L.ptr(eps), C.byref(t)))
+        for k, v in (("Uh", Uh), ("R", R), ("eps", eps)):
+            if v is not None:
+                out[k] = v
+        out["t"] = t.value
+        return out
+
+    def step_euler(self, params: "L.StepParams", n_steps=1):
+        st = L.StepStats()
+        L.check(self._lib.cfem_step_euler(self._h, C.byref(params), int(n_steps), C.byref(st)))
+        return st.as_dict()
+
     def time_kernel(self, kernel, flux, reps=20):
         ms, by = C.c_double(0.0), C.c_double(0.0)
         L.check(self._lib.cfem_time_kernel(self._h, int(kernel), _flux(flux), int(reps), C.byref(ms), C.byref(by)))

@@ -150,3 +150,43 @@ def solve_advection(domain, initial_condition=advection_initial_condition, veloc
         stats["eps"], stats["RH"], stats["h"], stats["dt"] = out["eps"], out["RH"], h, dt
         return uh, stats
     return uh
+
+
+# ---- compressible Euler (scheme defined by this repository, see DESIGN.md / oracle/euler.py) ----
+GAMMA = 1.4
+
+
+def sod_initial_condition(x, x0=1.0):
+    """(rho, p) = (1, 1) left of x0, (0.125, 0.1) right of it, fluid at rest -> (N, 4) conserved state.
+
+    gamma = 1.4 and the conserved variables follow ``Code/Compressible_euler/euler_RV.py:33,66-72``."""
+    left = x[0] < x0
+    rho = np.where(left, 1.0, 0.125)
+    p = np.where(left, 1.0, 0.1)
+    z = np.zeros_like(rho)
+    return np.stack([rho, z, z, p / (GAMMA - 1.0)], axis=1)
+
+
+def solve_euler(domain, initial_condition=sod_initial_condition, dt=None, num_steps=10, Cvel=0.5, Crv=4.0,
+                newton_rtol=1e-4, lin_rtol=1e-13, device=0, h=None, return_stats=False):
+    """4-component P1 RV Euler: BDF2 residual projection, nodal RV viscosity, Crank-Nicolson Newton.
+
+    Every component is Dirichlet (= its initial value) on the boundary."""
+    ctx = domain if isinstance(domain, Context) else Context.for_domain(domain, device=device)
+    if callable(initial_condition):
+        X = np.zeros((3, ctx.n))
+        X[0], X[1] = ctx.x[:, 0], ctx.x[:, 1]
+        U0 = np.ascontiguousarray(initial_condition(X), dtype=np.float64)
+    else:
+        U0 = np.ascontiguousarray(initial_condition, dtype=np.float64)
+    if U0.shape != (ctx.n, 4):
+        raise ValueError("the Euler state must have shape (N, 4): rho, m1, m2, E")
+    h = ctx.nodal_h() if h is None else _interpolate(ctx, h)
+    ctx.euler_state_set(Uh=U0, Un=U0, Uold=U0, Uoo=U0, bc_state=U0, h=h, t=0.0)
+    p = step_params(L.FLUX_BURGERS, dt, Cvel, Crv, scheme="bdf2", newton_rtol=newton_rtol, lin_rtol=lin_rtol)
+    stats = ctx.step_euler(p, num_steps)
+    out = ctx.euler_state_get(("Uh", "eps", "R"))
+    if return_stats:
+        stats.update(eps=out["eps"], R=out["R"], h=h)
+        return out["Uh"], stats
+    return out["Uh"]

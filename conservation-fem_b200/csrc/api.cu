@@ -263,7 +263,7 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   c->d_n2u = upload(c, hm.n2u);
   c->d_u2n = world == 1 ? upload(c, hm.u2n) : nullptr;  // user -> local is only a permutation on one GPU
   c->d_send_idx = upload(c, hm.send_idx);
-  c->d_sendbuf = dalloc<double>(c, 2 * (int64_t)hm.send_idx.size());
+  c->d_sendbuf = dalloc<double>(c, 4 * (int64_t)hm.send_idx.size());  // widest exchange: 4 components
   c->d_is_bnd = upload(c, hm.is_bnd);
   c->d_is_bc = dalloc<uint8_t>(c, nn);
   dm.is_bc = c->d_is_bc;
@@ -275,7 +275,7 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   std::vector<uint32_t>().swap(hm.v2c_code);
   std::vector<int32_t>().swap(hm.v2c_ptr);
   std::vector<int32_t>().swap(hm.tile_cells);
-  if (world > 1) CUDA_OK(cudaMallocHost((void**)&c->h_stage, 2 * nn * sizeof(double)));
+  if (world > 1) CUDA_OK(cudaMallocHost((void**)&c->h_stage, 4 * nn * sizeof(double)));
   for (int k = 0; k < 4; ++k) {
     c->mat[k].vals = dalloc<double>(c, hm.nnz);
     c->mat[k].dinv = dalloc<double>(c, nn);
@@ -290,6 +290,7 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   c->stage[2] = dalloc<double>(c, 2 * nn);
   c->stage[3] = c->stage[2] + nn;
   c->partials = dalloc<double>(c, 8 * (int64_t)kMaxPartials);
+  c->partials12 = dalloc<double>(c, 12 * (int64_t)kMaxPartials);
   c->scalars = dalloc<double>(c, 32);
   c->status = dalloc<int32_t>(c, 8);
   CUDA_OK(cudaMemsetAsync(c->status, 0, 8 * sizeof(int32_t), c->stream));
@@ -343,6 +344,7 @@ void cfem_destroy(cfem_ctx* c) {
   if (c->h_stage) cudaFreeHost(c->h_stage);
   for (void* p : c->allocs) cudaFree(p);
   for (cudaEvent_t e : c->prof.ev) cudaEventDestroy(e);
+  euler_free(c);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -757,6 +759,95 @@ int cfem_profile_end(cfem_ctx* c, double* ms_per_category, int64_t* launches_per
     launches_per_category[p.cat[e / 2]] += 1;
   }
   p.used = 0;
+  API_END
+}
+
+// ---- Euler system ---------------------------------------------
+// (Nn,4) caller arrays <-> local AoS device vectors; host staging through pageable copies.
+static void import_vec4(cfem_ctx* c, const double* user, double* dst) {
+  const int64_t nl = c->dm.nn;
+  std::vector<double> tmp;
+  const double* src = user;
+  std::vector<double> host_copy;
+  if (is_device_ptr(user)) {
+    host_copy.resize(4 * (size_t)c->dm.nn_global);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaMemcpy(host_copy.data(), user, host_copy.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    src = host_copy.data();
+  }
+  tmp.resize(4 * (size_t)nl);
+  const int32_t* n2u = c->hm.n2u.data();
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nl; ++i)
+    for (int k = 0; k < 4; ++k) tmp[4 * i + k] = src[4 * (int64_t)n2u[i] + k];
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaMemcpy(dst, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+}
+static void export_vec4(cfem_ctx* c, const double* internal, double* user) {
+  const int64_t no = c->dm.no;
+  std::vector<double> tmp(4 * (size_t)no);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaMemcpy(tmp.data(), internal, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (is_device_ptr(user)) CFEM_THROW(-1, "euler_state_get: outputs must be host arrays");
+  const int32_t* n2u = c->hm.n2u.data();
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < no; ++i)
+    for (int k = 0; k < 4; ++k) user[4 * (int64_t)n2u[i] + k] = tmp[4 * i + k];
+}
+
+int cfem_euler_state_set(cfem_ctx* c, const double* Uh, const double* Un, const double* Uold, const double* Uoo,
+                         const double* bc_state, const double* h, double t) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  double *dUh, *dUn, *dUold, *dUoo, *dG;
+  euler_state_ptrs(c, &dUh, &dUn, &dUold, &dUoo, &dG, nullptr);
+  if (Uh) import_vec4(c, Uh, dUh);
+  if (Un) import_vec4(c, Un, dUn);
+  if (Uold) import_vec4(c, Uold, dUold);
+  if (Uoo) import_vec4(c, Uoo, dUoo);
+  if (bc_state) import_vec4(c, bc_state, dG);
+  if (h) import_vec(c, h, c->h);
+  c->t = t;
+  euler_reset_predictions(c);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_euler_state_get(cfem_ctx* c, double* Uh, double* R, double* eps, double* t) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  double *dUh, *dR;
+  euler_state_ptrs(c, &dUh, nullptr, nullptr, nullptr, nullptr, &dR);
+  if (Uh) export_vec4(c, dUh, Uh);
+  if (R) export_vec4(c, dR, R);
+  if (eps) export_vec(c, c->eps, eps);
+  if (t) *t = c->t;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_step_euler(cfem_ctx* c, const cfem_step_params* p, int n_steps, cfem_step_stats* stats) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!p) CFEM_THROW(-1, "step_euler: null params");
+  if (!(p->dt > 0.0)) CFEM_THROW(-1, "step_euler: dt must be positive");
+  const Launches l0 = c->launches;
+  cfem_step_stats st{};
+  cudaEvent_t ev0, ev1;
+  CUDA_OK(cudaEventCreate(&ev0));
+  CUDA_OK(cudaEventCreate(&ev1));
+  CUDA_OK(cudaEventRecord(ev0, c->stream));
+  euler_steps(c, p, n_steps, &st);
+  CUDA_OK(cudaEventRecord(ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(ev1));
+  { float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); st.device_ms = ms; }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  st.time = c->t;
+  st.kernel_launches = c->launches.total - l0.total;
+  st.spmv_launches = c->launches.spmv - l0.spmv;
+  st.assembly_launches = c->launches.assembly - l0.assembly;
+  if (stats) *stats = st;
   API_END
 }
 

@@ -142,6 +142,39 @@ struct StiffnessOp {
   __device__ double node(int32_t, const double*) const { return 0.0; }
 };
 
+// Euler path (csrc/euler.cu): Cd[a][b] = int phi_a d_d phi_b = |K|/3 grad_d phi_b
+struct GradOp {
+  static constexpr int NV = 0;
+  static constexpr bool MAT = true;
+  int d;
+  __device__ void cell(const int32_t*, const CellGeom& g, int, double*, double* emat) const {
+    const double f = g.area * (1.0 / 3.0);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) emat[a * 3 + b] = f * (d == 0 ? g.gx[b] : g.gy[b]);
+  }
+  __device__ double node(int32_t, const double*) const { return 0.0; }
+};
+
+// S = M + coef K_eps (no Dirichlet handling: the Euler apply kernels do it by row)
+struct MassStiffOp {
+  static constexpr int NV = 0;
+  static constexpr bool MAT = true;
+  const double* eps;
+  double coef;
+  __device__ void cell(const int32_t* v, const CellGeom& g, int, double*, double* emat) const {
+    const double e = (eps[v[0]] + eps[v[1]] + eps[v[2]]) * (1.0 / 3.0);
+    const double m = g.area * (1.0 / 12.0), kf = coef * e * g.area;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        emat[a * 3 + b] = (a == b ? 2.0 * m : m) + kf * (g.gx[a] * g.gx[b] + g.gy[a] * g.gy[b]);
+  }
+  __device__ double node(int32_t, const double*) const { return 0.0; }
+};
+
 // b_i = sum_K h_K |K| / 3, h_K = shortest edge  (reference Code/Utils/helpers.py:18-31)
 struct NodalHOp {
   static constexpr int NV = 1;
@@ -462,6 +495,16 @@ void launch_mass(cfem_ctx* c, Matrix& M, bool bc) {
 void launch_stiffness(cfem_ctx* c, Matrix& K, const double* eps) {
   run_tiles(c, StiffnessOp{eps}, false, K.vals, K.dinv, nullptr);
   K.valid = true;
+}
+
+void launch_grad_matrix(cfem_ctx* c, int d, Matrix& C) {
+  run_tiles(c, GradOp{d}, false, C.vals, C.dinv, nullptr);
+  C.valid = true;
+}
+
+void launch_mass_stiff(cfem_ctx* c, const double* eps, double coef, Matrix& S) {
+  run_tiles(c, MassStiffOp{eps, coef}, false, S.vals, S.dinv, nullptr);
+  S.valid = true;
 }
 
 void launch_nodal_h_rhs(cfem_ctx* c, double* b) {

@@ -90,9 +90,12 @@ void comm_init(cfem_ctx* c, int rank, int world, const void* id128) {
 
 void comm_destroy(cfem_ctx* c) { c->nccl_comm = nullptr; }  // communicators are process-lifetime
 
-template <class T>
-__global__ void k_pack(const T* __restrict__ v, const int32_t* __restrict__ idx, T* __restrict__ out, int n) {
-  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) out[i] = v[idx[i]];
+__global__ void k_pack(const double* __restrict__ v, const int32_t* __restrict__ idx, double* __restrict__ out,
+                       int n, int width) {
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n * width; i += gridDim.x * kBlock) {
+    const int node = i / width, k = i - node * width;
+    out[i] = v[(size_t)idx[node] * width + k];
+  }
 }
 
 // ghosts of v <- owners' values.  width 1 (double) or 2 (double2, interleaved).
@@ -104,9 +107,8 @@ void halo_exchange(cfem_ctx* c, double* v, int width) {
   ProfScope ps(c, PROF_COMM);
   const int nsend = hm.send_ptr[npeer];
   if (nsend > 0) {
-    const int g = (nsend + kBlock - 1) / kBlock;
-    if (width == 1) k_pack<double><<<g, kBlock, 0, c->stream>>>(v, c->d_send_idx, c->d_sendbuf, nsend);
-    else k_pack<double2><<<g, kBlock, 0, c->stream>>>((const double2*)v, c->d_send_idx, (double2*)c->d_sendbuf, nsend);
+    const int g = (nsend * width + kBlock - 1) / kBlock;
+    k_pack<<<g, kBlock, 0, c->stream>>>(v, c->d_send_idx, c->d_sendbuf, nsend, width);
     LAUNCHED(c);
   }
   ncclComm_t comm = (ncclComm_t)c->nccl_comm;

@@ -144,6 +144,8 @@ struct cfem_ctx {
   double *wk[10] = {nullptr};
   double *stage[4] = {nullptr};   // staging for host<->device + permutation
   double *partials = nullptr;     // 8 * kMaxPartials doubles
+  double *partials12 = nullptr;   // 12 more slots (Euler: sum/min/max of 4 components)
+  void* euler = nullptr;          // lazily created Euler state (euler.cu)
   double *scalars = nullptr;      // small device scalar block
   int32_t* status = nullptr;      // device ints: [0]=done flag, [1]=iterations
   double* h_pinned = nullptr;     // pinned host scratch (small)

@@ -1,6 +1,8 @@
 // Host-callable launchers implemented in assembly.cu / linalg.cu / rv.cu.
 // All pointers are device pointers in INTERNAL (Hilbert) numbering.
 #pragma once
+#include <functional>
+
 #include "internal.h"
 
 namespace cfem {
@@ -24,6 +26,8 @@ void launch_cn_jacobian(cfem_ctx* c, int flux, double dt, const double* uh, cons
 void launch_adv_system(cfem_ctx* c, double dt, const double2* w, const double* eps,
                        const double* u_n, const double* g, Matrix& A, double* b);
 int assembly_grid(const cfem_ctx* c);
+void launch_grad_matrix(cfem_ctx* c, int d, Matrix& C);                                  // int phi_a d_d phi_b
+void launch_mass_stiff(cfem_ctx* c, const double* eps, double coef, Matrix& S);          // M + coef K_eps
 
 // ---- linear algebra (linalg.cu) ------------------------------------------------
 void launch_spmv(cfem_ctx* c, const Matrix& A, const double* x, double* y);
@@ -42,6 +46,12 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
                            int* predict);
 SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol,
                      double atol, int max_it, int* predict);
+// operator-generic BiCGStab (right Jacobi): apply(x, y, ndot, d0, d1, part0, part1, gated) computes y = A x
+// (refreshing the ghosts of x first), writes ndot fused dot-product partials and returns their count.
+using LinApply = std::function<int(const double*, double*, int, const double*, const double*, double*, double*, bool)>;
+SolveResult bicgstab_generic(cfem_ctx* c, int64_t n, int halo_width, const double* dinv, const LinApply& apply,
+                             double* const* work /*8 vectors*/, const double* b, double* x, double rtol, double atol,
+                             int max_it, int* predict);
 SolveResult gmres(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol,
                   double atol, int max_it, int* predict);
 double norm2(cfem_ctx* c, const double* v, int64_t n);  // synchronous
@@ -50,7 +60,7 @@ double norm2(cfem_ctx* c, const double* v, int64_t n);  // synchronous
 void comm_unique_id(void* out128);
 void comm_init(cfem_ctx* c, int rank, int world, const void* id128);
 void comm_destroy(cfem_ctx* c);
-void halo_exchange(cfem_ctx* c, double* v, int width = 1);
+void halo_exchange(cfem_ctx* c, double* v, int width = 1);   // width doubles per node (1, 2 or 4)
 // local reduce of each partial array to its element 0 + all-reduce; returns the partial count to use after
 int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int* ops /*0 sum,1 min,2 max*/, int npart);
 int allreduce_sum1(cfem_ctx* c, double* slot, int npart);
@@ -62,5 +72,11 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
                     const double* u_n, double* Rh, const double* h, const double2* w, double* eps);
 void launch_bc_values(cfem_ctx* c, int kind, double value, double t, const double* user_vals,
                       double* g);
+
+// ---- Euler system (euler.cu) -------------------------------------------------------------
+void euler_state_ptrs(cfem_ctx* c, double** Uh, double** Un, double** Uold, double** Uoo, double** G, double** R);
+void euler_reset_predictions(cfem_ctx* c);
+void euler_free(cfem_ctx* c);
+void euler_steps(cfem_ctx* c, const cfem_step_params* p, int n_steps, cfem_step_stats* st);
 
 }  // namespace cfem

@@ -589,19 +589,19 @@ k_bi_x(int64_t n, const double* __restrict__ y, const double* __restrict__ z, co
   }
 }
 
-SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
-                     int max_it, int* predict) {
-  const int64_t n = c->dm.no;
+SolveResult bicgstab_generic(cfem_ctx* c, int64_t n, int halo_width, const double* dinv, const LinApply& apply,
+                             double* const* work, const double* b, double* x, double rtol, double atol, int max_it,
+                             int* predict) {
   const bool dist = c->world > 1;
-  double *r = c->wk[0], *rhat = c->wk[1], *p = c->wk[2], *v = c->wk[3], *s = c->wk[4], *t = c->wk[5],
-         *y = c->wk[6], *z = c->wk[7];
+  double *r = work[0], *rhat = work[1], *p = work[2], *v = work[3], *s = work[4], *t = work[5], *y = work[6],
+         *z = work[7];
   double* part = c->partials;
-  const int gv = vec_grid(c, n), gs = spmv_grid(c);
+  const int gv = vec_grid(c, n);
   const double rtol2 = rtol * rtol, atol2 = atol * atol;
-  const int npv = dist ? 1 : gv, nps = dist ? 1 : gs;
+  const int npv = dist ? 1 : gv;  // partial counts seen by consumers of vector-kernel partials
   const int sum3[3] = {0, 0, 0};
-  launch_spmv(c, A, x, v);
-  { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_init<<<gv, kBlock, 0, c->stream>>>(n, b, v, A.dinv, r, rhat, p, y, part, c->status); LAUNCHED(c); }
+  apply(x, v, 0, nullptr, nullptr, nullptr, nullptr, false);
+  { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_init<<<gv, kBlock, 0, c->stream>>>(n, b, v, dinv, r, rhat, p, y, part, c->status); LAUNCHED(c); }
   { double* sl[3] = {part + P_RR * kMaxPartials, part + P_RZ0 * kMaxPartials, part + P_BB * kMaxPartials}; allreduce_partials(c, 3, sl, sum3, gv); }
   { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, npv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
   SolveResult res{0, 0.0, false};
@@ -609,13 +609,14 @@ SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, d
   while (it < max_it) {
     const int cur = it & 1;  // rho of this iteration lives in RZ[cur]
     if (it > 0) {
-      { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_p<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, p, y, part, npv, cur, c->scalars, c->status, rtol2, atol2);
-      LAUNCHED(c); }
+      ProfScope ps(c, PROF_KRYLOV_VEC);
+      k_bi_p<<<gv, kBlock, 0, c->stream>>>(n, r, v, dinv, p, y, part, npv, cur, c->scalars, c->status, rtol2, atol2);
+      LAUNCHED(c);
     }
-    spmv_dots<1>(c, A, y, v, rhat, nullptr, part + P_PQ * kMaxPartials, nullptr, true);
-    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_s<<<gv, kBlock, 0, c->stream>>>(n, r, v, A.dinv, s, z, part, npv, nps, cur, c->scalars, c->status); LAUNCHED(c); }
-    spmv_dots<2>(c, A, z, t, s, t, part + P_A * kMaxPartials, part + P_B * kMaxPartials, true);
-    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_x<<<gv, kBlock, 0, c->stream>>>(n, y, z, s, t, rhat, x, r, part, nps, cur, c->scalars, c->status); LAUNCHED(c); }
+    const int nps1 = apply(y, v, 1, rhat, nullptr, part + P_PQ * kMaxPartials, nullptr, true);
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_s<<<gv, kBlock, 0, c->stream>>>(n, r, v, dinv, s, z, part, npv, nps1, cur, c->scalars, c->status); LAUNCHED(c); }
+    const int nps2 = apply(z, t, 2, s, t, part + P_A * kMaxPartials, part + P_B * kMaxPartials, true);
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_x<<<gv, kBlock, 0, c->stream>>>(n, y, z, s, t, rhat, x, r, part, nps2, cur, c->scalars, c->status); LAUNCHED(c); }
     { double* sl[2] = {part + (cur ? P_RZ0 : P_RZ1) * kMaxPartials, part + P_RR * kMaxPartials}; allreduce_partials(c, 2, sl, sum3, gv); }
     ++it;
     if (it >= next_poll || it == max_it) {
@@ -626,9 +627,21 @@ SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, d
     }
   }
   if (!res.converged) { poll_done(c, res); }
-  halo_exchange(c, x);
+  halo_exchange(c, x, halo_width);
   if (predict) *predict = res.iters > 0 ? res.iters : 1;
   return res;
+}
+
+SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
+                     int max_it, int* predict) {
+  LinApply op = [&](const double* xin, double* yout, int ndot, const double* d0, const double* d1, double* p0,
+                    double* p1, bool gated) {
+    if (ndot == 0) spmv_dots<0>(c, A, xin, yout, nullptr, nullptr, nullptr, nullptr, gated);
+    else if (ndot == 1) spmv_dots<1>(c, A, xin, yout, d0, nullptr, p0, nullptr, gated);
+    else spmv_dots<2>(c, A, xin, yout, d0, d1, p0, p1, gated);
+    return c->world > 1 ? 1 : spmv_grid(c);
+  };
+  return bicgstab_generic(c, c->dm.no, 1, A.dinv, op, c->wk, b, x, rtol, atol, max_it, predict);
 }
 
 SolveResult gmres(cfem_ctx*, const Matrix&, const double*, double*, double, double, int, int*) {

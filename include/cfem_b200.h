@@ -211,6 +211,19 @@ int cfem_step_scalar(cfem_ctx* ctx, const cfem_step_params* p, int n_steps,
 int cfem_step_advection(cfem_ctx* ctx, const cfem_step_params* p, int n_steps, int first_gfem,
                         cfem_step_stats* stats);
 
+/* ---- (a-12) compressible Euler, 4-component P1 system -------------------------------------
+ * The reference's Code/Compressible_euler/euler_RV.py is a skeleton without an RV term; the
+ * scheme is defined by this repository (oracle/euler.py): conserved state
+ * U = (rho, m1, m2, E), gamma = 1.4 (euler_RV.py:33,66-72), group-FEM fluxes, BDF2 residual
+ * projection, eps = min(Cvel h max_P(|u|+c), Crv h^2 max_k max_P|R_k| / n_k), Crank-Nicolson +
+ * Newton (params: dt, Cvel, Crv, newton_*, lin_*), all components Dirichlet on the boundary.
+ * Arrays are (Nn,4) row-major in caller numbering; bc_state holds the Dirichlet values (read at
+ * the Dirichlet dofs); outputs must be host arrays. */
+int cfem_euler_state_set(cfem_ctx* ctx, const double* Uh, const double* Un, const double* Uold, const double* Uoo,
+                         const double* bc_state, const double* h, double t);
+int cfem_euler_state_get(cfem_ctx* ctx, double* Uh, double* R, double* eps, double* t);
+int cfem_step_euler(cfem_ctx* ctx, const cfem_step_params* p, int n_steps, cfem_step_stats* stats);
+
 /* ---- measurement hooks --------------------------------------------------
  * Average device time (ms, CUDA events on the context stream) of `reps`
  * back-to-back launches of one hot kernel on the resident state, and the

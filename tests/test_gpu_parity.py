@@ -243,6 +243,20 @@ def test_advection_steps():
         assert rel(stats["eps"], eps_ref) < 1e-8
 
 
+def test_euler_steps():
+    """a-12: 4-component Euler RV (scheme defined here; oracle = oracle/euler.py), Sod data."""
+    from oracle import euler as E
+
+    for x, c in (meshes.rectangle(40, 20, (0, 0), (2, 1)), meshes.jittered(30, 16, (0, 0), (2, 1))):
+        dt, n = 0.2 * 2 / 40, 8
+        st, sol = E.run_euler(x, c, dt, n)
+        U, stats = GS.solve_euler((x, c), dt=dt, num_steps=n, return_stats=True)
+        assert rel(U, st["Uh"]) < TOL_FIELD
+        assert stats["newton_iterations"] == sum(st["newton_its"])
+        assert rel(stats["eps"], st["eps"]) < 1e-8
+        assert U[:, 0].min() > 0.1 and np.all(np.isfinite(U))
+
+
 def test_determinism_bitwise():
     """Atomics-free assembly and fixed-order reductions: two runs agree bit for bit."""
     x, c = meshes.jittered(32, 32, (-2, -2), (2, 2))
