@@ -298,6 +298,7 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   CUDA_OK(cudaMallocHost((void**)&c->h_pinned, (64 + kMaxPartials) * sizeof(double)));
   CUDA_OK(cudaMallocHost((void**)&c->h_status, 8 * sizeof(int32_t)));
   if (hm.max_tile_cells > kTileCellCap || hm.max_tile_nnz > kTileNnzCap) CFEM_THROW(-1, "tile capacity exceeded");
+  comm_setup_exchange(c);
   launch_mass(c, c->mat[CFEM_MAT_MASS], false);
   // every boundary dof is a Dirichlet dof by default (reference loops: KPP_exact.py:85-89)
   apply_dirichlet(c, hm.bnd_user_sorted.data(), (int64_t)hm.bnd_user_sorted.size());
@@ -658,6 +659,7 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
   }
   CUDA_OK(cudaEventRecord(ev1, c->stream));
   CUDA_OK(cudaEventSynchronize(ev1));
+  comm_check(c);
   { float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); st.device_ms = ms; }
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
@@ -716,6 +718,7 @@ int cfem_step_advection(cfem_ctx* c, const cfem_step_params* p, int n_steps, int
   }
   CUDA_OK(cudaEventRecord(ev1, c->stream));
   CUDA_OK(cudaEventSynchronize(ev1));
+  comm_check(c);
   { float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); st.device_ms = ms; }
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
@@ -840,6 +843,7 @@ int cfem_step_euler(cfem_ctx* c, const cfem_step_params* p, int n_steps, cfem_st
   euler_steps(c, p, n_steps, &st);
   CUDA_OK(cudaEventRecord(ev1, c->stream));
   CUDA_OK(cudaEventSynchronize(ev1));
+  comm_check(c);
   { float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); st.device_ms = ms; }
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);

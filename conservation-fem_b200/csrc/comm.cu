@@ -8,8 +8,12 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
+#include <vector>
 
 #include "device_utils.cuh"
 #include "launch.h"
@@ -25,6 +29,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*GroupStart)();
   ncclResult_t (*GroupEnd)();
   const char* (*GetErrorString)(ncclResult_t);
@@ -47,6 +52,7 @@ static NcclApi& nccl() {
   SYM(Send, "ncclSend");
   SYM(Recv, "ncclRecv");
   SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
   SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd");
   SYM(GetErrorString, "ncclGetErrorString");
@@ -90,6 +96,219 @@ void comm_init(cfem_ctx* c, int rank, int world, const void* id128) {
 
 void comm_destroy(cfem_ctx* c) { c->nccl_comm = nullptr; }  // communicators are process-lifetime
 
+// ---------------------------------------------------------------- peer-memory path (NVLink, CUDA IPC)
+// NCCL's latency (~15 us per grouped send/recv or all-reduce) dominates at ~1M dofs per GPU, where
+// a step issues ~100 such operations.  Here every rank owns a "mailbox" in device memory that its
+// neighbours map through CUDA IPC; ONE kernel per exchange stores the halo values (or reduction
+// scalars) directly into the neighbours' mailboxes over NVLink, publishes a sequence number, waits
+// for the neighbours' numbers and copies the received values into place.  Two mailbox generations
+// (sequence parity) make the protocol race free: a rank can only be one exchange ahead of a
+// neighbour because each exchange waits for the neighbour's previous one.  Kernels on DIFFERENT
+// GPUs wait on one another; nothing waits on another kernel of the same GPU.  Spins are bounded
+// (~30 s) and raise an error flag instead of hanging.
+constexpr int kMaxWorld = 16;
+constexpr size_t kFlagBytes = 256;                         // halo_flag[16] | red_flag[16]  (uint64)
+constexpr size_t kRedBytes = 2 * kMaxWorld * 8 * sizeof(double);  // [parity][src rank][8 slots]
+
+struct P2PDev {  // passed to kernels by value
+  char* peer_base[kMaxWorld];   // by peer INDEX (halo) ...
+  char* rank_base[kMaxWorld];   // ... and by RANK (reductions; own rank -> local mailbox)
+  char* local;
+  int32_t dst_off[kMaxWorld];   // by peer index: where my values land in that peer's ghost segment (nodes)
+  int32_t peer_rank[kMaxWorld];
+  int npeer, world, rank;
+  size_t halo_off, halo_stride;  // bytes
+  const int32_t *send_ptr, *send_idx;
+  unsigned int* counter;         // kMaxWorld + 1 block counters
+  int* error;                    // pinned host flag
+  int64_t n_owned, n_ghost;
+};
+
+struct P2P {
+  P2PDev d;
+  unsigned long long halo_seq = 0, red_seq = 0;
+  int32_t* d_send_ptr = nullptr;
+  int* h_error = nullptr;
+};
+
+__device__ __forceinline__ bool wait_flag(const volatile unsigned long long* f, unsigned long long seq, int* error) {
+  const long long t0 = clock64();
+  while (*f < seq) {
+    if (clock64() - t0 > 60000000000LL) { *error = 1; return false; }
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_p2p_halo(const P2PDev a, double* __restrict__ v, const int width, const unsigned long long seq) {
+  const int parity = (int)(seq & 1);
+  // ---- push my owned values into every neighbour's mailbox
+  for (int k = 0; k < a.npeer; ++k) {
+    const int s0 = a.send_ptr[k], cnt = (a.send_ptr[k + 1] - s0) * width;
+    double* dst = (double*)(a.peer_base[k] + a.halo_off + parity * a.halo_stride) + (size_t)a.dst_off[k] * width;
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < cnt; i += gridDim.x * kBlock) {
+      const int node = i / width, kk = i - node * width;
+      dst[i] = v[(size_t)a.send_idx[s0 + node] * width + kk];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(a.counter, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < a.npeer) {
+    __threadfence_system();
+    *(volatile unsigned long long*)(a.peer_base[threadIdx.x] + 8 * a.rank) = seq;  // publish
+    if (threadIdx.x == 0) *a.counter = 0;
+  }
+  // ---- wait for the neighbours, then move their values into the ghost segment
+  if (threadIdx.x < a.npeer)
+    wait_flag((const volatile unsigned long long*)(a.local + 8 * a.peer_rank[threadIdx.x]), seq, a.error);
+  __syncthreads();
+  __threadfence_system();
+  const volatile double* src = (const volatile double*)(a.local + a.halo_off + parity * a.halo_stride);
+  double* ghost = v + (size_t)a.n_owned * width;
+  const int64_t total = a.n_ghost * width;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < total; i += (int64_t)gridDim.x * kBlock) ghost[i] = src[i];
+}
+
+struct SlotTable { double* p[8]; int op[8]; };
+
+// local reduction of each slot, exchange of the scalars with every rank, global reduction in rank order
+__global__ void __launch_bounds__(kBlock)
+k_p2p_allreduce(const P2PDev a, const SlotTable t, const int nslots, const int npart, const unsigned long long seq) {
+  __shared__ double red[9];
+  __shared__ bool last;
+  const int parity = (int)(seq & 1);
+  const int slot = blockIdx.x;
+  double* p = t.p[slot];
+  const int op = t.op[slot];
+  double s = op == 0 ? 0.0 : (op == 1 ? INFINITY : -INFINITY);
+  for (int i = threadIdx.x; i < npart; i += kBlock) {
+    const double x = p[i];
+    s = op == 0 ? s + x : (op == 1 ? fmin(s, x) : fmax(s, x));
+  }
+  s = op == 0 ? block_sum(s, red) : (op == 1 ? block_min(s, red) : block_max(s, red));
+  if (threadIdx.x < a.world) {
+    double* dst = (double*)(a.rank_base[threadIdx.x] + kFlagBytes) + ((size_t)parity * kMaxWorld + a.rank) * 8 + slot;
+    *(volatile double*)dst = s;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(a.counter + 1, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < a.world) {
+    __threadfence_system();
+    *(volatile unsigned long long*)(a.rank_base[threadIdx.x] + 128 + 8 * a.rank) = seq;
+    if (threadIdx.x == 0) a.counter[1] = 0;
+  }
+  if (threadIdx.x < a.world) wait_flag((const volatile unsigned long long*)(a.local + 128 + 8 * threadIdx.x), seq, a.error);
+  __syncthreads();
+  __threadfence_system();
+  if (threadIdx.x == 0) {
+    const volatile double* src = (const volatile double*)(a.local + kFlagBytes) + (size_t)parity * kMaxWorld * 8 + slot;
+    double r = src[0];
+    for (int q = 1; q < a.world; ++q) {
+      const double x = src[(size_t)q * 8];
+      r = op == 0 ? r + x : (op == 1 ? fmin(r, x) : fmax(r, x));
+    }
+    p[0] = r;
+  }
+}
+
+static void p2p_setup(cfem_ctx* c) {
+  const HostMesh& hm = c->hm;
+  const int world = c->world, rank = c->rank, npeer = (int)hm.peer_rank.size();
+  if (world > kMaxWorld) CFEM_THROW(-5, "peer-memory path supports at most 16 ranks");
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  P2P* pp = new P2P();
+  P2PDev& d = pp->d;
+  const int64_t ng = hm.nn - hm.n_owned;
+  d.halo_off = kFlagBytes + kRedBytes;
+  d.halo_stride = (((size_t)ng * 4 * sizeof(double)) + 255) / 256 * 256 + 256;
+  const size_t bytes = d.halo_off + 2 * d.halo_stride;
+  void* box = nullptr;
+  CUDA_OK(cudaMalloc(&box, bytes));
+  CUDA_OK(cudaMemset(box, 0, bytes));
+  c->allocs.push_back(box);
+  // ---- all-gather the IPC handles and the landing offsets (NCCL is the setup plumbing)
+  cudaIpcMemHandle_t mine;
+  CUDA_OK(cudaIpcGetMemHandle(&mine, box));
+  std::vector<int32_t> land(world, -1);  // where rank q's values land in MY ghost segment
+  for (int k = 0; k < npeer; ++k) land[hm.peer_rank[k]] = hm.recv_off[k] - (int32_t)hm.n_owned;
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + world * sizeof(int32_t);
+  std::vector<char> sendrec(rec), allrec(rec * world);
+  memcpy(sendrec.data(), &mine, sizeof(mine));
+  memcpy(sendrec.data() + sizeof(mine), land.data(), world * sizeof(int32_t));
+  char *dsend = nullptr, *drecv = nullptr;
+  CUDA_OK(cudaMalloc((void**)&dsend, rec));
+  CUDA_OK(cudaMalloc((void**)&drecv, rec * world));
+  CUDA_OK(cudaMemcpy(dsend, sendrec.data(), rec, cudaMemcpyHostToDevice));
+  NCCL_OK(nccl().AllGather(dsend, drecv, rec, ncclChar, comm, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaMemcpy(allrec.data(), drecv, rec * world, cudaMemcpyDeviceToHost));
+  cudaFree(dsend);
+  cudaFree(drecv);
+  d.local = (char*)box;
+  d.world = world;
+  d.rank = rank;
+  d.npeer = npeer;
+  d.n_owned = hm.n_owned;
+  d.n_ghost = ng;
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) { d.rank_base[q] = (char*)box; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, allrec.data() + q * rec, sizeof(h));
+    void* ptr = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    d.rank_base[q] = (char*)ptr;
+  }
+  for (int k = 0; k < npeer; ++k) {
+    const int q = hm.peer_rank[k];
+    d.peer_base[k] = d.rank_base[q];
+    d.peer_rank[k] = q;
+    const int32_t* their_land = (const int32_t*)(allrec.data() + q * rec + sizeof(cudaIpcMemHandle_t));
+    d.dst_off[k] = their_land[rank];
+    if (d.dst_off[k] < 0 && hm.send_ptr[k + 1] > hm.send_ptr[k]) CFEM_THROW(-5, "inconsistent halo lists between ranks");
+  }
+  CUDA_OK(cudaMalloc((void**)&pp->d_send_ptr, (npeer + 1) * sizeof(int32_t)));
+  CUDA_OK(cudaMemcpy(pp->d_send_ptr, hm.send_ptr.data(), (npeer + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  c->allocs.push_back(pp->d_send_ptr);
+  d.send_ptr = pp->d_send_ptr;
+  d.send_idx = c->d_send_idx;
+  CUDA_OK(cudaMalloc((void**)&d.counter, 2 * sizeof(unsigned int)));
+  CUDA_OK(cudaMemset(d.counter, 0, 2 * sizeof(unsigned int)));
+  c->allocs.push_back(d.counter);
+  CUDA_OK(cudaMallocHost((void**)&pp->h_error, sizeof(int)));
+  *pp->h_error = 0;
+  d.error = pp->h_error;
+  // every rank must have its mailbox mapped everywhere before the first exchange: one tiny all-reduce
+  double* tmp = c->partials;
+  NCCL_OK(nccl().AllReduce(tmp, tmp, 1, ncclDouble, ncclSum, comm, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->p2p = pp;
+}
+
+void comm_setup_exchange(cfem_ctx* c) {
+  if (c->world == 1) return;
+  const char* e = getenv("CFEM_COMM");
+  if (e && std::string(e) == "nccl") return;
+  p2p_setup(c);
+}
+
+void comm_check(cfem_ctx* c) {
+  if (c->p2p && *((P2P*)c->p2p)->h_error) {
+    *((P2P*)c->p2p)->h_error = 0;
+    CFEM_THROW(-5, "peer-memory exchange timed out waiting for a neighbour rank");
+  }
+}
+
 __global__ void k_pack(const double* __restrict__ v, const int32_t* __restrict__ idx, double* __restrict__ out,
                        int n, int width) {
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n * width; i += gridDim.x * kBlock) {
@@ -105,6 +324,17 @@ void halo_exchange(cfem_ctx* c, double* v, int width) {
   const int npeer = (int)hm.peer_rank.size();
   if (npeer == 0) return;
   ProfScope ps(c, PROF_COMM);
+  if (c->p2p) {
+    P2P* pp = (P2P*)c->p2p;
+    const int64_t work = std::max<int64_t>((int64_t)hm.send_idx.size(), hm.nn - hm.n_owned) * width;
+    int g = (int)((work + kBlock - 1) / kBlock);
+    if (g < 1) g = 1;
+    if (g > 32) g = 32;  // all CTAs must be co-resident: they wait for the neighbours
+    k_p2p_halo<<<g, kBlock, 0, c->stream>>>(pp->d, v, width, ++pp->halo_seq);
+    LAUNCHED(c);
+    c->halo_exchanges++;
+    return;
+  }
   const int nsend = hm.send_ptr[npeer];
   if (nsend > 0) {
     const int g = (nsend * width + kBlock - 1) / kBlock;
@@ -127,8 +357,6 @@ void halo_exchange(cfem_ctx* c, double* v, int width) {
 // Reduce each listed partial array (npart entries) to its element 0 locally, then all-reduce
 // those scalars over the ranks.  Returns the partial count consumers must use afterwards (1).
 // op: 0 sum, 1 min, 2 max.
-struct SlotTable { double* p[8]; int op[8]; };
-
 __global__ void __launch_bounds__(kBlock)
 k_reduce_slots(const SlotTable t, int npart) {
   __shared__ double red[9];
@@ -149,6 +377,13 @@ int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int*
   ProfScope ps(c, PROF_COMM);
   SlotTable t;
   for (int k = 0; k < nslots; ++k) { t.p[k] = slots[k]; t.op[k] = ops[k]; }
+  if (c->p2p) {
+    P2P* pp = (P2P*)c->p2p;
+    k_p2p_allreduce<<<nslots, kBlock, 0, c->stream>>>(pp->d, t, nslots, npart, ++pp->red_seq);
+    LAUNCHED(c);
+    c->allreduces++;
+    return 1;
+  }
   k_reduce_slots<<<nslots, kBlock, 0, c->stream>>>(t, npart); LAUNCHED(c);
   ncclComm_t comm = (ncclComm_t)c->nccl_comm;
   NCCL_OK(nccl().GroupStart());

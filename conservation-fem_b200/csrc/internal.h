@@ -156,6 +156,7 @@ struct cfem_ctx {
   // ---- distributed (world > 1): NCCL communicator + halo buffers
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
+  void* p2p = nullptr;              // peer-memory exchange state (comm.cu), null -> NCCL path
   int32_t* d_send_idx = nullptr;
   double* d_sendbuf = nullptr;      // 2 * total send count (double2 exchanges)
   double* h_stage = nullptr;        // pinned host staging, 2 * nn doubles

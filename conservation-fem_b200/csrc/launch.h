@@ -60,6 +60,8 @@ double norm2(cfem_ctx* c, const double* v, int64_t n);  // synchronous
 void comm_unique_id(void* out128);
 void comm_init(cfem_ctx* c, int rank, int world, const void* id128);
 void comm_destroy(cfem_ctx* c);
+void comm_setup_exchange(cfem_ctx* c);   // after the device arrays exist: maps the peer mailboxes (CUDA IPC)
+void comm_check(cfem_ctx* c);            // throws if a peer-memory exchange timed out
 void halo_exchange(cfem_ctx* c, double* v, int width = 1);   // width doubles per node (1, 2 or 4)
 // local reduce of each partial array to its element 0 + all-reduce; returns the partial count to use after
 int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int* ops /*0 sum,1 min,2 max*/, int npart);
