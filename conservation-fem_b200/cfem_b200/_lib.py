@@ -98,6 +98,7 @@ SIGNATURES = {
     "cfem_spmv": (_I, [_P, _I, _P, _P]),
     "cfem_solve": (_I, [_P, _I, _I, _P, _P, _D, _D, _I, C.POINTER(_I), C.POINTER(_D)]),
     "cfem_state_set": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _D]),
+    "cfem_state_update": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _D]),
     "cfem_state_get": (_I, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(_D)]),
     "cfem_step_scalar": (_I, [_P, C.POINTER(StepParams), _I, _P, C.POINTER(StepStats)]),
     "cfem_step_advection": (_I, [_P, C.POINTER(StepParams), _I, _I, C.POINTER(StepStats)]),

@@ -207,10 +207,15 @@ class Context:
         return x
 
     # -- (a-10)
-    def state_set(self, uh=None, u_n=None, u_old=None, u_oo=None, RH=None, h=None, w=None, t=0.0):
+    def state_set(self, uh=None, u_n=None, u_old=None, u_oo=None, RH=None, h=None, w=None, t=0.0,
+                  keep_predictions=False):
+        """Load state fields (None: leave as is).  ``keep_predictions`` keeps the solvers' iteration-count
+        predictions from the previous call (a negative ``t`` is not meaningful, so the flag rides on a
+        separate entry point: ``cfem_state_update``)."""
         args = [_field(a) for a in (uh, u_n, u_old, u_oo, RH, h, w)]
         self._keep = args
-        L.check(self._lib.cfem_state_set(self._h, *[L.ptr(a) for a in args], float(t)))
+        fn = self._lib.cfem_state_update if keep_predictions else self._lib.cfem_state_set
+        L.check(fn(self._h, *[L.ptr(a) for a in args], float(t)))
 
     def state_get(self, names=("uh",), out=None):
         """Return dict name -> array for names among uh,u_n,u_old,u_oo,RH,eps (+ 't')."""

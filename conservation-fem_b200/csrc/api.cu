@@ -260,6 +260,8 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   dm.tile_node = upload(c, hm.tile_node);
   dm.tile_cellptr = upload(c, hm.tile_cellptr);
   dm.tile_cells = upload(c, hm.tile_cells);
+  dm.tile_order = upload(c, hm.tile_order);
+  dm.n_interior = hm.n_interior_tiles;
   c->d_n2u = upload(c, hm.n2u);
   c->d_u2n = world == 1 ? upload(c, hm.u2n) : nullptr;  // user -> local is only a permutation on one GPU
   c->d_send_idx = upload(c, hm.send_idx);
@@ -543,9 +545,8 @@ int cfem_solve(cfem_ctx* c, int which, int solver, const double* b, double* x_io
   API_END
 }
 
-int cfem_state_set(cfem_ctx* c, const double* uh, const double* u_n, const double* u_old, const double* u_oo,
-                   const double* RH, const double* h, const double* w, double t) {
-  API_BEGIN
+static void state_load(cfem_ctx* c, const double* uh, const double* u_n, const double* u_old, const double* u_oo,
+                       const double* RH, const double* h, const double* w, double t) {
   CUDA_OK(cudaSetDevice(c->device));
   if (uh) import_vec(c, uh, c->uh);
   if (u_n) import_vec(c, u_n, c->u_n);
@@ -555,10 +556,23 @@ int cfem_state_set(cfem_ctx* c, const double* uh, const double* u_n, const doubl
   if (h) import_vec(c, h, c->h);
   if (w) import_vec2(c, w, c->w);
   c->t = t;
+}
+
+int cfem_state_set(cfem_ctx* c, const double* uh, const double* u_n, const double* u_old, const double* u_oo,
+                   const double* RH, const double* h, const double* w, double t) {
+  API_BEGIN
+  state_load(c, uh, u_n, u_old, u_oo, RH, h, w, t);
   // iteration-count predictions restart with the state, so a run is a pure function of its inputs
   c->pcg_predict = 28;
   c->krylov_predict = 8;
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int cfem_state_update(cfem_ctx* c, const double* uh, const double* u_n, const double* u_old, const double* u_oo,
+                      const double* RH, const double* h, const double* w, double t) {
+  API_BEGIN
+  state_load(c, uh, u_n, u_old, u_oo, RH, h, w, t);  // stream-ordered: no host sync needed before the next call
   API_END
 }
 

@@ -17,6 +17,7 @@
 
 #include "device_utils.cuh"
 #include "launch.h"
+#include "p2p.cuh"
 
 namespace cfem {
 
@@ -106,37 +107,42 @@ void comm_destroy(cfem_ctx* c) { c->nccl_comm = nullptr; }  // communicators are
 // neighbour because each exchange waits for the neighbour's previous one.  Kernels on DIFFERENT
 // GPUs wait on one another; nothing waits on another kernel of the same GPU.  Spins are bounded
 // (~30 s) and raise an error flag instead of hanging.
-constexpr int kMaxWorld = 16;
-constexpr size_t kFlagBytes = 256;                         // halo_flag[16] | red_flag[16]  (uint64)
-constexpr size_t kRedBytes = 2 * kMaxWorld * 8 * sizeof(double);  // [parity][src rank][8 slots]
-
-struct P2PDev {  // passed to kernels by value
-  char* peer_base[kMaxWorld];   // by peer INDEX (halo) ...
-  char* rank_base[kMaxWorld];   // ... and by RANK (reductions; own rank -> local mailbox)
-  char* local;
-  int32_t dst_off[kMaxWorld];   // by peer index: where my values land in that peer's ghost segment (nodes)
-  int32_t peer_rank[kMaxWorld];
-  int npeer, world, rank;
-  size_t halo_off, halo_stride;  // bytes
-  const int32_t *send_ptr, *send_idx;
-  unsigned int* counter;         // kMaxWorld + 1 block counters
-  int* error;                    // pinned host flag
-  int64_t n_owned, n_ghost;
-};
-
 struct P2P {
   P2PDev d;
   unsigned long long halo_seq = 0, red_seq = 0;
   int32_t* d_send_ptr = nullptr;
+  int32_t* d_peer_rank = nullptr;
   int* h_error = nullptr;
 };
 
-__device__ __forceinline__ bool wait_flag(const volatile unsigned long long* f, unsigned long long seq, int* error) {
-  const long long t0 = clock64();
-  while (*f < seq) {
-    if (clock64() - t0 > 60000000000LL) { *error = 1; return false; }
+// push only: the consumer (a SpMV-type kernel) does the waiting, and only in its boundary-tile CTAs
+__global__ void __launch_bounds__(kBlock)
+k_p2p_push(const P2PDev a, const double* __restrict__ v, const int width, const unsigned long long seq,
+           const int32_t* __restrict__ status) {
+  const int parity = (int)(seq & 1);
+  if (!(status && status[0])) {
+    for (int k = 0; k < a.npeer; ++k) {
+      const int s0 = a.send_ptr[k], cnt = (a.send_ptr[k + 1] - s0) * width;
+      double* dst = (double*)(a.peer_base[k] + a.halo_off + parity * a.halo_stride) + (size_t)a.dst_off[k] * width;
+      for (int i = blockIdx.x * kBlock + threadIdx.x; i < cnt; i += gridDim.x * kBlock) {
+        const int node = i / width, kk = i - node * width;
+        dst[i] = v[(size_t)a.send_idx[s0 + node] * width + kk];
+      }
+    }
   }
-  return true;
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(a.counter, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < a.npeer) {
+    __threadfence_system();
+    *(volatile unsigned long long*)(a.peer_base[threadIdx.x] + 8 * a.rank) = seq;  // publish (even when gated: keeps the sequence aligned)
+    if (threadIdx.x == 0) *a.counter = 0;
+  }
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -280,6 +286,9 @@ static void p2p_setup(cfem_ctx* c) {
   CUDA_OK(cudaMalloc((void**)&pp->d_send_ptr, (npeer + 1) * sizeof(int32_t)));
   CUDA_OK(cudaMemcpy(pp->d_send_ptr, hm.send_ptr.data(), (npeer + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
   c->allocs.push_back(pp->d_send_ptr);
+  CUDA_OK(cudaMalloc((void**)&pp->d_peer_rank, (npeer + 1) * sizeof(int32_t)));
+  CUDA_OK(cudaMemcpy(pp->d_peer_rank, hm.peer_rank.data(), npeer * sizeof(int32_t), cudaMemcpyHostToDevice));
+  c->allocs.push_back(pp->d_peer_rank);
   d.send_ptr = pp->d_send_ptr;
   d.send_idx = c->d_send_idx;
   CUDA_OK(cudaMalloc((void**)&d.counter, 2 * sizeof(unsigned int)));
@@ -352,6 +361,40 @@ void halo_exchange(cfem_ctx* c, double* v, int width) {
   }
   NCCL_OK(nccl().GroupEnd());
   c->halo_exchanges++;
+}
+
+// Producer half of a halo exchange for a vector that a SpMV-type kernel is about to read: pushes
+// the owned boundary values to the neighbours and returns where the consumer finds its ghosts.
+// (NCCL mode: does the whole exchange and returns an empty GhostSrc.)
+GhostSrc halo_push(cfem_ctx* c, double* v, bool gated) {
+  GhostSrc g;
+  if (c->world == 1) {
+    // measurement hook: CFEM_FORCE_GHOST=1 runs the ghost-aware kernel variants on one GPU (no ghosts, no waiting)
+    static const bool force = getenv("CFEM_FORCE_GHOST") != nullptr;
+    if (force) { g.mbox = c->stage[0]; g.flags = (const char*)c->status; g.seq = 0; g.npeer = 0; }
+    return g;
+  }
+  static const bool fused = !(getenv("CFEM_HALO") && std::string(getenv("CFEM_HALO")) == "exchange");
+  if (!c->p2p || !fused) { halo_exchange(c, v, 1); return g; }
+  const HostMesh& hm = c->hm;
+  const int npeer = (int)hm.peer_rank.size();
+  if (npeer == 0) return g;
+  ProfScope ps(c, PROF_COMM);
+  P2P* pp = (P2P*)c->p2p;
+  const unsigned long long seq = ++pp->halo_seq;
+  int grid = (int)((hm.send_idx.size() + kBlock - 1) / kBlock);
+  if (grid < 1) grid = 1;
+  if (grid > 32) grid = 32;
+  k_p2p_push<<<grid, kBlock, 0, c->stream>>>(pp->d, v, 1, seq, gated ? c->status : nullptr);
+  LAUNCHED(c);
+  c->halo_exchanges++;
+  g.mbox = (const double*)(pp->d.local + pp->d.halo_off + (seq & 1) * pp->d.halo_stride);
+  g.flags = pp->d.local;
+  g.seq = seq;
+  g.npeer = npeer;
+  g.peer_rank = pp->d_peer_rank;
+  g.error = pp->d.error;
+  return g;
 }
 
 // Reduce each listed partial array (npart entries) to its element 0 locally, then all-reduce

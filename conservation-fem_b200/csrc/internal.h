@@ -56,6 +56,8 @@ struct HostMesh {
   std::vector<int32_t> tile_node;         // ntiles+1
   std::vector<int32_t> tile_cellptr;      // ntiles+1
   std::vector<int32_t> tile_cells;        // concatenated cell lists
+  std::vector<int32_t> tile_order;        // tiles whose rows touch no ghost column first, the others last
+  int n_interior_tiles = 0;
   std::vector<uint8_t> is_bnd;            // nn
   std::vector<int32_t> bnd_user_sorted;   // boundary dofs, user ids ascending
   int max_row = 0, max_tile_cells = 0, max_tile_nnz = 0;
@@ -81,6 +83,8 @@ struct DevMesh {
   const int32_t* tile_node;
   const int32_t* tile_cellptr;
   const int32_t* tile_cells;
+  const int32_t* tile_order;   // interior tiles first (identity on one GPU)
+  int n_interior;              // number of tiles that need no ghost value
   const uint8_t* is_bc;    // current Dirichlet flags
 };
 

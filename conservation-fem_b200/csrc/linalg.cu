@@ -14,6 +14,7 @@
 
 #include "device_utils.cuh"
 #include "launch.h"
+#include "p2p.cuh"
 
 namespace cfem {
 
@@ -134,15 +135,20 @@ k_spmv(const int64_t nn, const int32_t* __restrict__ rowptr, const int32_t* __re
   }
 }
 
+// ghost entries of the input vector come from the mailbox when the exchange was push-only
+// (a select on the base pointer, then ONE load: predicated twin loads cost ~30% of the kernel)
+#define XG(vec, col) ((GHOST ? (((col) >= no) ? mbox_shifted : (vec)) : (vec))[col])
+
 // CSR-stream SpMV: a CTA takes one assembly tile (<= kTileNodes consecutive rows,
 // <= kTileNnzCap entries).  Every thread streams entries p, p+256, ... of the
 // tile's contiguous CSR segment (vals/colidx fully coalesced, loads independent
 // -> deep memory-level parallelism), multiplies by the gathered x[col] and parks
 // the product in shared memory; then thread r sums row r's products in column
 // order.  Fixed order, no atomics.
-template <int NDOT>
+template <int NDOT, bool GHOST>
 __global__ void __launch_bounds__(kTileNodes)
-k_spmv_stream(const int ntiles, const int32_t* __restrict__ tile_node, const int32_t* __restrict__ rowptr,
+k_spmv_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ tile_order, const int n_interior,
+              const int ntiles, const int32_t* __restrict__ tile_node, const int32_t* __restrict__ rowptr,
               const int32_t* __restrict__ colidx, const double* __restrict__ vals, const double* __restrict__ x,
               double* __restrict__ y, const double* __restrict__ d0, const double* __restrict__ d1,
               double* __restrict__ part0, double* __restrict__ part1, const int32_t* __restrict__ status) {
@@ -152,7 +158,11 @@ k_spmv_stream(const int ntiles, const int32_t* __restrict__ tile_node, const int
   __shared__ double red[9];
   const int tid = threadIdx.x;
   double acc0 = 0.0, acc1 = 0.0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  bool waited = false;
+  const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;  // mbox_shifted[col] == mailbox[col - no]
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tile = GHOST ? tile_order[t] : t;
+    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
     const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
     for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i];
     __syncthreads();
@@ -163,13 +173,13 @@ k_spmv_stream(const int ntiles, const int32_t* __restrict__ tile_node, const int
     for (; p + 3 * kTileNodes < cnt; p += 4 * kTileNodes) {
       const int c0 = ci[p], c1 = ci[p + kTileNodes], c2 = ci[p + 2 * kTileNodes], c3 = ci[p + 3 * kTileNodes];
       const double v0 = v[p], v1 = v[p + kTileNodes], v2 = v[p + 2 * kTileNodes], v3 = v[p + 3 * kTileNodes];
-      const double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+      const double x0 = XG(x, c0), x1 = XG(x, c1), x2 = XG(x, c2), x3 = XG(x, c3);
       prod[p] = v0 * x0;
       prod[p + kTileNodes] = v1 * x1;
       prod[p + 2 * kTileNodes] = v2 * x2;
       prod[p + 3 * kTileNodes] = v3 * x3;
     }
-    for (; p < cnt; p += kTileNodes) prod[p] = v[p] * x[ci[p]];
+    for (; p < cnt; p += kTileNodes) { const int cc = ci[p]; prod[p] = v[p] * XG(x, cc); }
     __syncthreads();
     if (tid < nrows) {
       const int a = rp[tid] - start, b = rp[tid + 1] - start;
@@ -212,12 +222,20 @@ static inline int spmv_grid(const cfem_ctx* c) {
 template <int NDOT>
 static void spmv_dots(cfem_ctx* c, const Matrix& A, const double* x, double* y, const double* d0,
                       const double* d1, double* p0, double* p1, bool gated) {
-  halo_exchange(c, const_cast<double*>(x));  // ghosts of the input vector (no-op on one GPU)
+  GhostSrc gsrc;
+  if (spmv_mode() == 0) gsrc = halo_push(c, const_cast<double*>(x), gated);  // producer half; the kernel waits in its boundary CTAs
+  else halo_exchange(c, const_cast<double*>(x));
   ProfScope ps(c, PROF_SPMV);
-  if (spmv_mode() == 0)
-    k_spmv_stream<NDOT><<<spmv_grid(c), kTileNodes, 0, c->stream>>>(c->dm.ntiles, c->dm.tile_node, c->dm.rowptr,
-                                                                    c->dm.colidx, A.vals, x, y, d0, d1, p0, p1,
-                                                                    gated ? c->status : nullptr);
+  if (spmv_mode() == 0 && gsrc.mbox)
+    k_spmv_stream<NDOT, true><<<spmv_grid(c), kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior,
+                                                                          c->dm.ntiles, c->dm.tile_node, c->dm.rowptr,
+                                                                          c->dm.colidx, A.vals, x, y, d0, d1, p0, p1,
+                                                                          gated ? c->status : nullptr);
+  else if (spmv_mode() == 0)
+    k_spmv_stream<NDOT, false><<<spmv_grid(c), kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior,
+                                                                           c->dm.ntiles, c->dm.tile_node, c->dm.rowptr,
+                                                                           c->dm.colidx, A.vals, x, y, d0, d1, p0, p1,
+                                                                           gated ? c->status : nullptr);
   else
     k_spmv<8, NDOT><<<spmv_grid(c), kBlock, 0, c->stream>>>(c->dm.no, c->dm.rowptr, c->dm.colidx, A.vals, x, y, d0,
                                                             d1, p0, p1, gated ? c->status : nullptr);
@@ -240,9 +258,10 @@ void launch_spmv(cfem_ctx* c, const Matrix& A, const double* x, double* y) {
 // no inner products: one fused kernel per iteration (SpMV + residual + update), no
 // reductions, no host round trips until the final check.
 //   r_k = b - M x_k ; z_k = D^-1 r_k ; d_k = c1 d_{k-1} + c2 z_k ; x_{k+1} = x_k + d_k
-template <bool FIRST>
+template <bool FIRST, bool GHOST>
 __global__ void __launch_bounds__(kTileNodes)
-k_cheb_stream(const int ntiles, const int32_t* __restrict__ tile_node, const int32_t* __restrict__ rowptr,
+k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ tile_order, const int n_interior,
+              const int ntiles, const int32_t* __restrict__ tile_node, const int32_t* __restrict__ rowptr,
               const int32_t* __restrict__ colidx, const double* __restrict__ vals, const double* __restrict__ dinv,
               const double* __restrict__ b, const double* __restrict__ xk, double* __restrict__ xn,
               double* __restrict__ d, const double c1, const double c2, double* __restrict__ part_rr,
@@ -252,7 +271,11 @@ k_cheb_stream(const int ntiles, const int32_t* __restrict__ tile_node, const int
   __shared__ double red[9];
   const int tid = threadIdx.x;
   double rr = 0.0, bb = 0.0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  bool waited = false;
+  const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;  // mbox_shifted[col] == mailbox[col - no]
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tile = GHOST ? tile_order[t] : t;
+    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
     const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
     for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i];
     __syncthreads();
@@ -263,13 +286,13 @@ k_cheb_stream(const int ntiles, const int32_t* __restrict__ tile_node, const int
     for (; p + 3 * kTileNodes < cnt; p += 4 * kTileNodes) {
       const int c0 = ci[p], c1i = ci[p + kTileNodes], c2i = ci[p + 2 * kTileNodes], c3 = ci[p + 3 * kTileNodes];
       const double v0 = v[p], v1 = v[p + kTileNodes], v2 = v[p + 2 * kTileNodes], v3 = v[p + 3 * kTileNodes];
-      const double x0 = xk[c0], x1 = xk[c1i], x2 = xk[c2i], x3 = xk[c3];
+      const double x0 = XG(xk, c0), x1 = XG(xk, c1i), x2 = XG(xk, c2i), x3 = XG(xk, c3);
       prod[p] = v0 * x0;
       prod[p + kTileNodes] = v1 * x1;
       prod[p + 2 * kTileNodes] = v2 * x2;
       prod[p + 3 * kTileNodes] = v3 * x3;
     }
-    for (; p < cnt; p += kTileNodes) prod[p] = v[p] * xk[ci[p]];
+    for (; p < cnt; p += kTileNodes) { const int cc = ci[p]; prod[p] = v[p] * XG(xk, cc); }
     __syncthreads();
     if (tid < nrows) {
       const int a = rp[tid] - start, e = rp[tid + 1] - start;
@@ -319,19 +342,22 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
   if (target > max_it) target = max_it;
   while (true) {
     for (; it < target; ++it) {
-      halo_exchange(c, xa);
+      const GhostSrc gsrc = halo_push(c, xa, false);
       ProfScope ps(c, PROF_CHEB);
+#define CHEB_LAUNCH(FIRST, GHOST, C1, C2, PBB)                                                                   \
+  k_cheb_stream<FIRST, GHOST><<<gs, kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior, \
+      c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, A.dinv, b, xa, xb, d, C1, C2,              \
+      part + P_RR * kMaxPartials, PBB)
       if (it == 0) {
-        k_cheb_stream<true><<<gs, kTileNodes, 0, c->stream>>>(c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
-                                                             A.vals, A.dinv, b, xa, xb, d, 0.0, 1.0 / theta,
-                                                             part + P_RR * kMaxPartials, part + P_BB * kMaxPartials);
+        if (gsrc.mbox) CHEB_LAUNCH(true, true, 0.0, 1.0 / theta, part + P_BB * kMaxPartials);
+        else CHEB_LAUNCH(true, false, 0.0, 1.0 / theta, part + P_BB * kMaxPartials);
       } else {
         const double rho_new = 1.0 / (2.0 * sigma1 - rho);
-        k_cheb_stream<false><<<gs, kTileNodes, 0, c->stream>>>(c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
-                                                              A.vals, A.dinv, b, xa, xb, d, rho_new * rho,
-                                                              2.0 * rho_new / delta, part + P_RR * kMaxPartials, nullptr);
+        if (gsrc.mbox) CHEB_LAUNCH(false, true, rho_new * rho, 2.0 * rho_new / delta, nullptr);
+        else CHEB_LAUNCH(false, false, rho_new * rho, 2.0 * rho_new / delta, nullptr);
         rho = rho_new;
       }
+#undef CHEB_LAUNCH
       LAUNCHED(c);
       c->launches.spmv++;
       if (it == 0) np_bb = allreduce_sum1(c, part + P_BB * kMaxPartials, gs);

@@ -394,6 +394,19 @@ static void build_tiles(HostMesh& hm, const std::vector<int32_t>& v2c, const std
     if ((int)cur.size() > kTileCellCap) CFEM_THROW(-1, "node valence exceeds tile capacity");
   }
   close_tile(no);
+  // interior tiles (no ghost column in any row) first: SpMV-type kernels start on them while the
+  // neighbours' halo values are still in flight
+  const int nt = (int)hm.tile_node.size() - 1;
+  std::vector<int32_t> interior, boundary;
+  for (int t = 0; t < nt; ++t) {
+    bool needs_ghost = false;
+    for (int p = hm.rowptr[hm.tile_node[t]]; p < hm.rowptr[hm.tile_node[t + 1]] && !needs_ghost; ++p)
+      needs_ghost = hm.colidx[p] >= no;
+    (needs_ghost ? boundary : interior).push_back(t);
+  }
+  hm.n_interior_tiles = (int)interior.size();
+  hm.tile_order = interior;
+  hm.tile_order.insert(hm.tile_order.end(), boundary.begin(), boundary.end());
 }
 
 int32_t user_to_local(const HostMesh& hm, int64_t user_dof) {

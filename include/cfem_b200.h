@@ -198,6 +198,10 @@ typedef struct cfem_step_stats {
  * (cfem_nodal_h output, or caller supplied); w = advection velocity (Nn,2). */
 int cfem_state_set(cfem_ctx* ctx, const double* uh, const double* u_n, const double* u_old,
                    const double* u_oo, const double* RH, const double* h, const double* w, double t);
+/* same as cfem_state_set but keeps the solvers' iteration-count predictions (a caller that re-sends its
+ * host-resident fields every step); cfem_state_set restarts them so that a run is a pure function of its inputs */
+int cfem_state_update(cfem_ctx* ctx, const double* uh, const double* u_n, const double* u_old,
+                      const double* u_oo, const double* RH, const double* h, const double* w, double t);
 int cfem_state_get(cfem_ctx* ctx, double* uh, double* u_n, double* u_old, double* u_oo,
                    double* RH, double* eps, double* t);
 
