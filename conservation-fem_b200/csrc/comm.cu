@@ -236,8 +236,18 @@ static void p2p_setup(cfem_ctx* c) {
   P2P* pp = new P2P();
   P2PDev& d = pp->d;
   const int64_t ng = hm.nn - hm.n_owned;
+  // The mailbox layout must be IDENTICAL on every rank (a sender computes addresses inside its
+  // neighbours' mailboxes): size the two halo generations by the largest ghost count of any rank.
+  int64_t* dng = nullptr;
+  CUDA_OK(cudaMalloc((void**)&dng, sizeof(int64_t)));
+  CUDA_OK(cudaMemcpy(dng, &ng, sizeof(int64_t), cudaMemcpyHostToDevice));
+  NCCL_OK(nccl().AllReduce(dng, dng, 1, ncclInt64, ncclMax, comm, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  int64_t ng_max = 0;
+  CUDA_OK(cudaMemcpy(&ng_max, dng, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  cudaFree(dng);
   d.halo_off = kFlagBytes + kRedBytes;
-  d.halo_stride = (((size_t)ng * 4 * sizeof(double)) + 255) / 256 * 256 + 256;
+  d.halo_stride = (((size_t)ng_max * 4 * sizeof(double)) + 255) / 256 * 256 + 256;
   const size_t bytes = d.halo_off + 2 * d.halo_stride;
   void* box = nullptr;
   CUDA_OK(cudaMalloc(&box, bytes));

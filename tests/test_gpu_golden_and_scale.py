@@ -131,10 +131,12 @@ def test_two_gpu_partition_parity():
 
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run tests/dist_gpu_check.py under torchrun on a multi-GPU box)")
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run tests/dist_gpu_check.py under torchrun on a multi-GPU box)")
     script = os.path.join(os.path.dirname(__file__), "dist_gpu_check.py")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    nproc = 4 if ngpu >= 4 else 2   # 4 ranks exercise unequal ghost counts and 3 neighbours per rank
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
                         "--master-addr", "127.0.0.1", "--master-port", "29533", script],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
