@@ -295,14 +295,17 @@ k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
     for (; p < cnt; p += kTileNodes) { const int cc = ci[p]; prod[p] = v[p] * XG(xk, cc); }
     __syncthreads();
     if (tid < nrows) {
+      const int row = n0 + tid;
+      // operands of the update are requested before the row sum so their latency overlaps it
+      const double bi = b[row], di = dinv[row], xo = xk[row];
+      const double dprev = FIRST ? 0.0 : d[row];
       const int a = rp[tid] - start, e = rp[tid + 1] - start;
       double s = 0.0;
       for (int k = a; k < e; ++k) s += prod[k];
-      const int row = n0 + tid;
-      const double bi = b[row], r = bi - s, z = dinv[row] * r;
-      const double dk = FIRST ? c2 * z : c1 * d[row] + c2 * z;
+      const double r = bi - s, z = di * r;
+      const double dk = FIRST ? c2 * z : c1 * dprev + c2 * z;
       d[row] = dk;
-      xn[row] = xk[row] + dk;
+      xn[row] = xo + dk;
       rr += r * r;
       if (FIRST) bb += bi * bi;
     }
