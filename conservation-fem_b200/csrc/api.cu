@@ -253,8 +253,10 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   dm.ntiles = (int)hm.tile_node.size() - 1;
   dm.xy = (const double2*)upload(c, hm.xy);
   dm.cells = upload(c, hm.cells);
-  dm.rowptr = upload(c, hm.rowptr);
-  dm.colidx = upload(c, hm.colidx);
+  { std::vector<int32_t> rp(hm.rowptr), ci(hm.colidx);  // padded copies for the aligned bulk-copy windows
+    rp.resize(rp.size() + 8, rp.back()); ci.resize(ci.size() + 8, 0);
+    dm.rowptr = upload(c, rp);
+    dm.colidx = upload(c, ci); }
   dm.v2c_ptr = upload(c, hm.v2c_ptr);
   dm.v2c_code = upload(c, hm.v2c_code);
   dm.tile_node = upload(c, hm.tile_node);
@@ -279,7 +281,7 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   std::vector<int32_t>().swap(hm.tile_cells);
   if (world > 1) CUDA_OK(cudaMallocHost((void**)&c->h_stage, 4 * nn * sizeof(double)));
   for (int k = 0; k < 4; ++k) {
-    c->mat[k].vals = dalloc<double>(c, hm.nnz);
+    c->mat[k].vals = dalloc<double>(c, hm.nnz + 8);  // +8: 16-byte aligned bulk-copy windows may overrun the last tile
     c->mat[k].dinv = dalloc<double>(c, nn);
   }
   double** state[] = {&c->uh, &c->u_n, &c->u_old, &c->u_oo, &c->RH, &c->eps, &c->h, &c->g, &c->fluxn};

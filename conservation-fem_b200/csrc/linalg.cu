@@ -202,17 +202,207 @@ k_spmv_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
   }
 }
 
-static int g_spmv_mode = -1;  // 0 = stream (default), 1 = sub-warp per row (CFEM_SPMV=subwarp)
+// ---- row epilogues shared by the tile kernels
+template <int NDOT>
+struct EpSpmv {  // y = A x with NDOT fused dot products
+  static constexpr int NACC = NDOT;
+  double* y;
+  const double *d0, *d1;
+  double *p0, *p1;
+  __device__ __forceinline__ void row(int row, double s, double& a0, double& a1) const {
+    y[row] = s;
+    if (NDOT >= 1) a0 += s * (d0 == y ? s : d0[row]);
+    if (NDOT >= 2) a1 += s * (d1 == y ? s : d1[row]);
+  }
+};
+
+template <bool FIRST>
+struct EpCheb {  // one Chebyshev iteration of the mass solve (see k_cheb_stream)
+  static constexpr int NACC = FIRST ? 2 : 1;
+  const double *dinv, *b, *xk;
+  double *xn, *d;
+  double c1, c2;
+  double *p0, *p1;  // ||r||^2 , ||b||^2 partials
+  __device__ __forceinline__ void row(int row, double s, double& a0, double& a1) const {
+    const double bi = b[row], r = bi - s, z = dinv[row] * r;
+    const double dk = FIRST ? c2 * z : c1 * d[row] + c2 * z;
+    d[row] = dk;
+    xn[row] = xk[row] + dk;
+    a0 += r * r;
+    if (FIRST) a1 += bi * bi;
+  }
+};
+
+// ---------------------------------------------------------------- TMA-staged tile SpMV
+// Same arithmetic as k_spmv_stream / k_cheb_stream, with the DRAM stream moved off the warps:
+// one elected thread issues three 1-D bulk copies per tile (cp.async.bulk -> UBLKCP: vals, colidx,
+// rowptr slice; 16-byte aligned windows around the tile's CSR segment) into one of two
+// shared-memory buffers and an mbarrier counts the bytes in.  While the CTA gathers x, multiplies
+// and row-sums tile t out of buffer (t&1), the copy engine is already filling the other buffer
+// with tile t+1, and the metadata of tile t+2 is in flight in registers.
+constexpr int kTmaVals = (kTileNnzCap + 2) * 8;                 // window may start one entry early
+constexpr int kTmaCols = ((kTileNnzCap + 4) * 4 + 15) / 16 * 16;
+constexpr int kTmaRows = ((kTileNodes + 1 + 4) * 4 + 15) / 16 * 16;
+constexpr int kTmaBuf = kTmaVals + kTmaCols + kTmaRows;
+static_assert(kTmaVals % 16 == 0 && kTmaBuf % 16 == 0, "bulk copies need 16-byte aligned destinations");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// bounded wait: returns false (and the kernel flags an error) instead of hanging the GPU
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  for (int spin = 0; spin < (1 << 26); ++spin) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+template <class EP, bool GHOST>
+__global__ void __launch_bounds__(kTileNodes)
+k_tile_spmv_tma(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ tile_order, const int n_interior,
+                const int ntiles, const int32_t* __restrict__ tile_node, const int32_t* __restrict__ rowptr,
+                const int32_t* __restrict__ colidx, const double* __restrict__ vals, const double* __restrict__ x,
+                const EP ep, const int32_t* __restrict__ status, int* __restrict__ error) {
+  if (status && status[0]) return;
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ double red[9];
+  const int tid = threadIdx.x;
+  const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;
+  double acc0 = 0.0, acc1 = 0.0;
+  bool waited = false;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  struct Meta { int n0, nrows, start, cnt; };
+  auto load_meta = [&](int t) {
+    Meta m{0, 0, 0, 0};
+    if (t < ntiles) {
+      const int tile = GHOST ? tile_order[t] : t;
+      m.n0 = tile_node[tile];
+      const int n1 = tile_node[tile + 1];
+      m.nrows = n1 - m.n0;
+      m.start = rowptr[m.n0];
+      m.cnt = rowptr[n1] - m.start;
+    }
+    return m;
+  };
+  auto issue = [&](int b, const Meta& m) {  // thread 0 only
+    unsigned char* base = tma_smem + b * kTmaBuf;
+    const uint32_t bv = (uint32_t)(((m.cnt + (m.start & 1)) * 8 + 15) & ~15);
+    const uint32_t bc = (uint32_t)(((m.cnt + (m.start & 3)) * 4 + 15) & ~15);
+    const uint32_t br = (uint32_t)(((m.nrows + 1 + (m.n0 & 3)) * 4 + 15) & ~15);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to this buffer are done
+    mbar_expect_tx(&bars[b], bv + bc + br);
+    bulk_g2s(base, vals + (m.start & ~1), bv, &bars[b]);
+    bulk_g2s(base + kTmaVals, colidx + (m.start & ~3), bc, &bars[b]);
+    bulk_g2s(base + kTmaVals + kTmaCols, rowptr + (m.n0 & ~3), br, &bars[b]);
+  };
+
+  int t = blockIdx.x;
+  Meta cur = load_meta(t);
+  if (t < ntiles && tid == 0) issue(0, cur);
+  Meta nxt = load_meta(t + gridDim.x);
+  int buf = 0;
+  uint32_t phase[2] = {0, 0};
+  for (; t < ntiles; t += gridDim.x) {
+    const bool has_next = t + (int)gridDim.x < ntiles;
+    if (has_next && tid == 0) issue(buf ^ 1, nxt);
+    const Meta nxt2 = load_meta(t + 2 * (int)gridDim.x);  // in flight during this tile's arithmetic
+    if (!mbar_wait(&bars[buf], phase[buf])) { if (tid == 0 && error) *error = 2; return; }
+    phase[buf] ^= 1;
+    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
+    unsigned char* base = tma_smem + buf * kTmaBuf;
+    double* sv = (double*)base + (cur.start & 1);
+    const int32_t* sc = (const int32_t*)(base + kTmaVals) + (cur.start & 3);
+    const int32_t* sr = (const int32_t*)(base + kTmaVals + kTmaCols) + (cur.n0 & 3);
+    const int cnt = cur.cnt;
+    int p = tid;
+    for (; p + 3 * kTileNodes < cnt; p += 4 * kTileNodes) {
+      const int c0 = sc[p], c1 = sc[p + kTileNodes], c2 = sc[p + 2 * kTileNodes], c3 = sc[p + 3 * kTileNodes];
+      const double x0 = XG(x, c0), x1 = XG(x, c1), x2 = XG(x, c2), x3 = XG(x, c3);
+      sv[p] *= x0;
+      sv[p + kTileNodes] *= x1;
+      sv[p + 2 * kTileNodes] *= x2;
+      sv[p + 3 * kTileNodes] *= x3;
+    }
+    for (; p < cnt; p += kTileNodes) { const int cc = sc[p]; sv[p] *= XG(x, cc); }
+    __syncthreads();
+    if (tid < cur.nrows) {
+      const int a = sr[tid] - cur.start, e = sr[tid + 1] - cur.start;
+      double s = 0.0;
+      for (int k = a; k < e; ++k) s += sv[k];
+      ep.row(cur.n0 + tid, s, acc0, acc1);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my generic writes precede the next bulk copy into this buffer
+    __syncthreads();
+    buf ^= 1;
+    cur = nxt;
+    nxt = nxt2;
+  }
+  if (EP::NACC >= 1) {
+    acc0 = block_sum(acc0, red);
+    if (tid == 0) ep.p0[blockIdx.x] = acc0;
+  }
+  if (EP::NACC >= 2) {
+    acc1 = block_sum(acc1, red);
+    if (tid == 0) ep.p1[blockIdx.x] = acc1;
+  }
+}
+
+static int tma_grid(const cfem_ctx* c) {  // persistent: SMs x CTAs that fit (2 x 31 KB of shared memory each)
+  const int64_t cap = (int64_t)c->sm_count * 3;
+  return (int)(c->dm.ntiles < cap ? c->dm.ntiles : cap);
+}
+
+template <class EP>
+static void launch_tile_spmv(cfem_ctx* c, const GhostSrc& gsrc, const Matrix& A, const double* x, const EP& ep, bool gated) {
+  static bool configured[2] = {false, false};
+  const size_t smem = 2 * (size_t)kTmaBuf;
+  const int32_t* st = gated ? c->status : nullptr;
+  int* err = (int*)(c->h_status + 6);  // pinned, host-visible
+  if (gsrc.mbox) {
+    if (!configured[1]) { CUDA_OK(cudaFuncSetAttribute(k_tile_spmv_tma<EP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[1] = true; }
+    k_tile_spmv_tma<EP, true><<<tma_grid(c), kTileNodes, smem, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior, c->dm.ntiles,
+                                                                           c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, x, ep, st, err);
+  } else {
+    if (!configured[0]) { CUDA_OK(cudaFuncSetAttribute(k_tile_spmv_tma<EP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[0] = true; }
+    k_tile_spmv_tma<EP, false><<<tma_grid(c), kTileNodes, smem, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior, c->dm.ntiles,
+                                                                            c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, x, ep, st, err);
+  }
+}
+
+static int g_spmv_mode = -1;  // 0 = tile kernels (default), 1 = sub-warp per row (CFEM_SPMV=subwarp)
+static int g_spmv_tma = 0;    // tile kernels: CFEM_SPMV=tma selects the TMA-staged variant (measured slower)
 static inline int spmv_mode() {
   if (g_spmv_mode < 0) {
     const char* e = getenv("CFEM_SPMV");
     g_spmv_mode = (e && std::string(e) == "subwarp") ? 1 : 0;
+    g_spmv_tma = (e && std::string(e) == "tma") ? 1 : 0;
   }
   return g_spmv_mode;
 }
 
 static inline int spmv_grid(const cfem_ctx* c) {
   const int64_t cap = (int64_t)c->sm_count * 8;
+  if (spmv_mode() == 0 && g_spmv_tma) return tma_grid(c);
   if (spmv_mode() == 0) return (int)(c->dm.ntiles < cap ? c->dm.ntiles : cap);
   const int64_t rows_per_block = (kBlock / 32) * 4;
   int64_t b = (c->dm.no + rows_per_block - 1) / rows_per_block;
@@ -226,7 +416,9 @@ static void spmv_dots(cfem_ctx* c, const Matrix& A, const double* x, double* y, 
   if (spmv_mode() == 0) gsrc = halo_push(c, const_cast<double*>(x), gated);  // producer half; the kernel waits in its boundary CTAs
   else halo_exchange(c, const_cast<double*>(x));
   ProfScope ps(c, PROF_SPMV);
-  if (spmv_mode() == 0 && gsrc.mbox)
+  if (spmv_mode() == 0 && g_spmv_tma)
+    launch_tile_spmv(c, gsrc, A, x, EpSpmv<NDOT>{y, d0, d1, p0, p1}, gated);
+  else if (spmv_mode() == 0 && gsrc.mbox)
     k_spmv_stream<NDOT, true><<<spmv_grid(c), kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior,
                                                                           c->dm.ntiles, c->dm.tile_node, c->dm.rowptr,
                                                                           c->dm.colidx, A.vals, x, y, d0, d1, p0, p1,
@@ -351,7 +543,13 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
   k_cheb_stream<FIRST, GHOST><<<gs, kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior, \
       c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, A.dinv, b, xa, xb, d, C1, C2,              \
       part + P_RR * kMaxPartials, PBB)
-      if (it == 0) {
+      if (g_spmv_tma && it == 0) {
+        launch_tile_spmv(c, gsrc, A, xa, EpCheb<true>{A.dinv, b, xa, xb, d, 0.0, 1.0 / theta, part + P_RR * kMaxPartials, part + P_BB * kMaxPartials}, false);
+      } else if (g_spmv_tma) {
+        const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+        launch_tile_spmv(c, gsrc, A, xa, EpCheb<false>{A.dinv, b, xa, xb, d, rho_new * rho, 2.0 * rho_new / delta, part + P_RR * kMaxPartials, nullptr}, false);
+        rho = rho_new;
+      } else if (it == 0) {
         if (gsrc.mbox) CHEB_LAUNCH(true, true, 0.0, 1.0 / theta, part + P_BB * kMaxPartials);
         else CHEB_LAUNCH(true, false, 0.0, 1.0 / theta, part + P_BB * kMaxPartials);
       } else {
