@@ -9,4 +9,4 @@ from ._lib import CfemError, LIB_PATH  # noqa: F401
 from .context import Context, step_params  # noqa: F401
 from .solvers import (NodalFunction, solve_advection, solve_burgers, solve_kpp,  # noqa: F401
                       kpp_initial_condition, burgers_initial_condition, advection_initial_condition,
-                      advection_velocity, advection_dt, solve_euler, sod_initial_condition)
+                      advection_velocity, advection_dt, solve_euler, sod_initial_condition, l2_error, convergence_rate)

@@ -90,6 +90,7 @@ SIGNATURES = {
     "cfem_nodal_h": (_I, [_P, _P, _D, _I, C.POINTER(_I)]),
     "cfem_rv_residual": (_I, [_P, _I, _I, _D, _P, _P, _P, _P, _I, _P, _D, _I, C.POINTER(_I)]),
     "cfem_rv_epsilon": (_I, [_P, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P]),
+    "cfem_si_epsilon": (_I, [_P, _I, _D, _D, _I, _P, _P, _P, _P, _P]),
     "cfem_assemble_advection": (_I, [_P, _D, _P, _P, _P, _P, _P]),
     "cfem_assemble_cn_residual": (_I, [_P, _I, _D, _P, _P, _P, _P, _P]),
     "cfem_assemble_cn_jacobian": (_I, [_P, _I, _D, _P, _P]),

@@ -158,6 +158,15 @@ class Context:
                                           L.ptr(u_n), L.ptr(Rh), L.ptr(h), L.ptr(w), L.ptr(eps)))
         return eps
 
+    # -- (f-1) smoothness indicator
+    def si_epsilon(self, flux, Cm, floor, u_n, h, w=None, use_bc=True, want_psi=False):
+        eps = np.empty(self.n)
+        psi = np.empty(self.n) if want_psi else None
+        u_n, h, w = _field(u_n), _field(h), _field(w)
+        L.check(self._lib.cfem_si_epsilon(self._h, _flux(flux), float(Cm), float(floor), int(bool(use_bc)), L.ptr(u_n),
+                                          L.ptr(h), L.ptr(w), L.ptr(psi), L.ptr(eps)))
+        return (eps, psi) if want_psi else eps
+
     # -- (a-7, a-8)
     def assemble_advection(self, dt, w, eps, u_n, bc_values=None):
         b = np.empty(self.n)

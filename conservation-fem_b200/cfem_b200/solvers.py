@@ -190,3 +190,21 @@ def solve_euler(domain, initial_condition=sod_initial_condition, dt=None, num_st
         stats.update(eps=out["eps"], R=out["R"], h=h)
         return out["Uh"], stats
     return out["Uh"]
+
+
+# ---- (f-2) L2-error functional and convergence-rate fit -------------------------------------------------
+def l2_error(domain, uh, u_ref):
+    """``sqrt(assemble_scalar((uh - u_ref)**2 * dx))`` with both fields in P1 (mass-matrix norm on the GPU).
+
+    The reference integrates against a P3 interpolant of the exact solution
+    (``Code/Linear_advection/RV_node_convergence.py:49,239``); here ``u_ref`` is its P1 interpolant (nodal values
+    or a callable of ``x`` with shape ``(3, N)``)."""
+    ctx = domain if isinstance(domain, Context) else Context.for_domain(domain)
+    d = _interpolate(ctx, uh) - _interpolate(ctx, u_ref)
+    Md = ctx.spmv(L.MAT_MASS, d)
+    return float(np.sqrt(max(float(d @ Md), 0.0)))
+
+
+def convergence_rate(hs, errors):
+    """Slope of log10(error) over log10(h) (``Code/Utils/PDE_plot.py:71-73``)."""
+    return float(np.polyfit(np.log10(np.asarray(hs, dtype=float)), np.log10(np.asarray(errors, dtype=float)), 1)[0])

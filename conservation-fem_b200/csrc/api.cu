@@ -456,6 +456,27 @@ int cfem_rv_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
   API_END
 }
 
+int cfem_si_epsilon(cfem_ctx* c, int flux, double Cm, double floor_, int use_bc, const double* u_n, const double* h,
+                    const double* w, double* psi_out, double* eps_out) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!u_n || !h || !eps_out) CFEM_THROW(-1, "si_epsilon: null argument");
+  if (!c->unit_stiffness.vals) {
+    c->unit_stiffness.vals = dalloc<double>(c, c->dm.nnz + 8);
+    c->unit_stiffness.dinv = dalloc<double>(c, c->dm.nn);
+  }
+  if (!c->unit_stiffness.valid) launch_stiffness(c, c->unit_stiffness, nullptr);
+  import_vec(c, u_n, c->u_n);
+  import_vec(c, h, c->h);
+  if (w) import_vec2(c, w, c->w);
+  launch_si_epsilon(c, flux, Cm, floor_, use_bc != 0, c->unit_stiffness, c->u_n, c->h, w ? c->w : nullptr,
+                    psi_out ? c->wk[9] : nullptr, c->eps);
+  export_vec(c, c->eps, eps_out);
+  if (psi_out) export_vec(c, c->wk[9], psi_out);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
 int cfem_assemble_advection(cfem_ctx* c, double dt, const double* w, const double* eps, const double* u_n,
                             const double* bc_values, double* b_out) {
   API_BEGIN

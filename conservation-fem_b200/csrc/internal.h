@@ -139,6 +139,7 @@ struct cfem_ctx {
   int64_t nbc_user = 0;           // size of the caller's list
   std::vector<int32_t> bc_user;   // caller's Dirichlet set
   cfem::Matrix mat[4];
+  cfem::Matrix unit_stiffness;      // int grad u . grad v, assembled on first use (SI viscosity)
   // state vectors (internal order)
   double *uh = nullptr, *u_n = nullptr, *u_old = nullptr, *u_oo = nullptr, *RH = nullptr,
          *eps = nullptr, *h = nullptr, *g = nullptr, *fluxn = nullptr;

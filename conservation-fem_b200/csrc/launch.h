@@ -74,6 +74,8 @@ int allreduce_sum1(cfem_ctx* c, double* slot, int npart);
 void launch_stats(cfem_ctx* c, const double* v);
 void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv, const double* uh,
                     const double* u_n, double* Rh, const double* h, const double2* w, double* eps);
+void launch_si_epsilon(cfem_ctx* c, int flux, double Cm, double floor_, bool use_bc, const Matrix& K1, const double* u,
+                       const double* h, const double2* w, double* psi, double* eps);
 void launch_bc_values(cfem_ctx* c, int kind, double value, double t, const double* user_vals,
                       double* g);
 

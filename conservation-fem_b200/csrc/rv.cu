@@ -221,6 +221,56 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
   CFEM_THROW(-1, "rv_epsilon: unknown variant");
 }
 
+// ---------------------------------------------------------------- smoothness indicator (SI.py:38-67,147-192)
+template <int FLUX>
+__global__ void __launch_bounds__(kBlock)
+k_si_epsilon(int64_t no, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+             const double* __restrict__ K, const uint8_t* __restrict__ is_bc, const double* __restrict__ u,
+             const double* __restrict__ h, const double2* __restrict__ w, double Cm, double floor_,
+             double* __restrict__ psi_out, double* __restrict__ eps) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < no; i += (int64_t)gridDim.x * kBlock) {
+    const double ui = u[i];
+    double num = 0.0, den = 0.0;
+    if (!(is_bc && is_bc[i])) {  // an identity row only sees itself: both sums stay 0
+      const int p1 = rowptr[i + 1];
+      for (int p = rowptr[i]; p < p1; ++p) {
+        const int j = colidx[p];
+        if (is_bc && is_bc[j]) continue;  // zeroed Dirichlet column
+        const double du = u[j] - ui, b = K[p];
+        num += b * du;
+        den += fabs(b) * fabs(du);
+      }
+    }
+    const double alpha = fabs(num) / fmax(den, floor_);
+    const double psi = 1.0 / (1.0 + exp(-20.0 * (alpha - 0.5)));
+    double fn;
+    if (FLUX == CFEM_FLUX_ADVECTION) { const double2 wi = w[i]; fn = sqrt(__dadd_rn(__dmul_rn(wi.x, wi.x), __dmul_rn(wi.y, wi.y))); }
+    else fn = beta_of<FLUX == CFEM_FLUX_ADVECTION ? CFEM_FLUX_BURGERS : FLUX>(ui);
+    if (psi_out) psi_out[i] = psi;
+    eps[i] = psi * Cm * h[i] * fn;
+  }
+}
+
+void launch_si_epsilon(cfem_ctx* c, int flux, double Cm, double floor_, bool use_bc, const Matrix& K1, const double* u,
+                       const double* h, const double2* w, double* psi, double* eps) {
+  ProfScope ps(c, PROF_RV);
+  const int64_t no = c->dm.no;
+  const int g = vec_grid(c, no);
+  const uint8_t* bc = use_bc ? c->dm.is_bc : nullptr;
+  if (flux == CFEM_FLUX_ADVECTION) {
+    if (!w) CFEM_THROW(-1, "si_epsilon: velocity field w is required");
+    k_si_epsilon<CFEM_FLUX_ADVECTION><<<g, kBlock, 0, c->stream>>>(no, c->dm.rowptr, c->dm.colidx, K1.vals, bc, u, h, w, Cm, floor_, psi, eps);
+  } else if (flux == CFEM_FLUX_BURGERS) {
+    k_si_epsilon<CFEM_FLUX_BURGERS><<<g, kBlock, 0, c->stream>>>(no, c->dm.rowptr, c->dm.colidx, K1.vals, bc, u, h, w, Cm, floor_, psi, eps);
+  } else if (flux == CFEM_FLUX_KPP) {
+    k_si_epsilon<CFEM_FLUX_KPP><<<g, kBlock, 0, c->stream>>>(no, c->dm.rowptr, c->dm.colidx, K1.vals, bc, u, h, w, Cm, floor_, psi, eps);
+  } else {
+    CFEM_THROW(-1, "si_epsilon: unknown flux");
+  }
+  LAUNCHED(c);
+  halo_exchange(c, eps);
+}
+
 // ---------------------------------------------------------------- Dirichlet data
 // Exact solution of the 2-D Burgers Riemann problem, same branch order and
 // operation order as the reference (Code/Burgers_equation/Exact_Burger_RV.py:37-66),

@@ -131,6 +131,14 @@ int cfem_rv_epsilon(cfem_ctx* ctx, int variant, int flux, double Cvel, double Cr
                     const double* uh, const double* u_n, double* Rh,
                     const double* h, const double* w, double* eps_out);
 
+/* ---- (f-1) smoothness-indicator viscosity   Code/Utils/SI.py:38-67,147-192 ----------------
+ * alpha_i = |sum_j b_ij (u_j - u_i)| / max(sum_j |b_ij||u_j - u_i|, floor) over the unit stiffness
+ * matrix b, psi = 1/(1+exp(-20(alpha-0.5))), eps_i = psi Cm h_i ||f'(u_i)|| (flux BURGERS/KPP) or
+ * psi Cm h_i ||w_i|| (flux ADVECTION).  use_bc != 0: b carries identity Dirichlet rows/cols, as the
+ * reference assembles it (Exact_Burger_SI.py:169-172).  psi_out may be NULL. */
+int cfem_si_epsilon(cfem_ctx* ctx, int flux, double Cm, double floor, int use_bc, const double* u_n,
+                    const double* h, const double* w, double* psi_out, double* eps_out);
+
 /* ---- (a-7, a-8) assembly ----------------------------------------------
  * Matrices are written into the context (CFEM_MAT_SYSTEM); fetch values with
  * cfem_matrix_values.  Vectors go to caller memory.

@@ -158,3 +158,36 @@ def smooth_vector_literal(u, patches, l):
         d = len(adj) - 1
         u[node] = (s + (l - 1) * d * u[node]) / (l * d)
     return u
+
+
+# ------------------------------------------------------------------ smoothness indicator
+def sigmoid_activation(alpha, s=20.0, x0=0.5):
+    """``SI.sigmoid_activation`` (``Code/Utils/SI.py:30-33``)."""
+    return 1.0 / (1.0 + np.exp(-s * (alpha - x0)))
+
+
+def si_epsilon(K, u_n, h, fnorm, Cm, floor, bc_nodes=None):
+    """``SI.get_epsilon_nonlinear`` / ``get_epsilon_linear`` (``Code/Utils/SI.py:38-67,147-192``).
+
+    ``K``: unit stiffness matrix (scipy CSR); with ``bc_nodes`` its Dirichlet rows/cols are identity,
+    as in the reference loop (``Exact_Burger_SI.py:169-172`` assembles it with ``bcs=[bc]``).
+    ``fnorm``: nodal ``||f'(u_n)||`` (nonlinear) or ``||w||`` (linear).  Returns (eps, psi)."""
+    import scipy.sparse as sp
+
+    K = sp.csr_matrix(K)
+    n = K.shape[0]
+    if bc_nodes is not None and len(bc_nodes):
+        keep = np.ones(n)
+        keep[bc_nodes] = 0.0
+        D = sp.diags(keep)
+        K = (D @ K @ D + sp.diags(1.0 - keep)).tocsr()
+    K.sort_indices()
+    rows = np.repeat(np.arange(n), np.diff(K.indptr))
+    du = u_n[K.indices] - u_n[rows]
+    num = np.zeros(n)
+    den = np.zeros(n)
+    np.add.at(num, rows, K.data * du)
+    np.add.at(den, rows, np.abs(K.data) * np.abs(du))
+    alpha = np.abs(num) / np.maximum(den, floor)
+    psi = sigmoid_activation(alpha)
+    return psi * Cm * h * fnorm, psi

@@ -124,6 +124,29 @@ def test_kpp_4M_cells_unstructured_steps():
     ctx.close()
 
 
+def test_advection_convergence_rate_on_gpu():
+    """(f-2) L2-error functional + rate fit.  Published: 2.25 / 2.11 for smooth / continuous data
+    (full rotation on a disk); here a short rotation on a square, rate > 1.7."""
+    from oracle.solvers import advection_initial_condition
+
+    hs, errs = [], []
+    for n in (32, 64, 128):
+        x, c = meshes.rectangle(n, n, (-1, -1), (1, 1))
+        ctx = Context((x, c))
+        w = GS.advection_velocity(np.vstack([x.T, np.zeros(x.shape[0])])).T.copy()
+        dt = GS.advection_dt(w, 2.0 / n) / 2
+        steps = int(round(0.1 / dt))
+        uh = GS.solve_advection(ctx, dt=dt, num_steps=steps)
+        th = 2 * np.pi * dt * steps
+        R = np.array([[np.cos(th), np.sin(th)], [-np.sin(th), np.cos(th)]])
+        exact = advection_initial_condition(x @ R.T) * (np.linalg.norm(x, axis=1) < 0.8)
+        got = uh.x.array * (np.linalg.norm(x, axis=1) < 0.8)
+        hs.append(2.0 / n)
+        errs.append(GS.l2_error(ctx, got, exact))
+        ctx.close()
+    assert GS.convergence_rate(hs, errs) > 1.7, (hs, errs)
+
+
 def test_two_gpu_partition_parity():
     """Domain-decomposed run (NCCL halo exchange + all-reduce) against the oracle; needs >= 2 GPUs."""
     import subprocess

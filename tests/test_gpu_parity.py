@@ -197,6 +197,23 @@ def test_krylov_vs_lu(case, solver):
     assert ctx.last_relres <= 1e-13
 
 
+def test_si_epsilon(case):
+    """(f-1) smoothness-indicator viscosity, SI.py:38-67 / 147-192."""
+    _, x, c, ctx, m = case
+    uh, u_n, _, _, rng = fields(m)
+    h = np.abs(rng.normal(size=m.n)) + 0.01
+    K = p1.stiffness_matrix(x, c)
+    for use_bc in (True, False):
+        bcn = m.bnd if use_bc else None
+        ref, psi_ref = rv.si_epsilon(K, u_n, h, rv.beta_burgers(u_n), 1.0, 1e-8, bcn)
+        got, psi = ctx.si_epsilon("burgers", 1.0, 1e-8, u_n, h, use_bc=use_bc, want_psi=True)
+        assert rel(got, ref) < 1e-11 and rel(psi, psi_ref) < 1e-11
+    w = S.advection_velocity(x)
+    ref, _ = rv.si_epsilon(K, u_n, h, np.sqrt(w[:, 0] ** 2 + w[:, 1] ** 2), 0.5, 1e-8, m.bnd)
+    got = ctx.si_epsilon("advection", 0.5, 1e-8, u_n, h, w=w)
+    assert rel(got, ref) < 1e-11
+
+
 def test_device_pointer_arguments(case):
     """torch is only the buffer allocator: CUDA tensors go through unchanged."""
     import torch
