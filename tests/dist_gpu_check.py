@@ -71,6 +71,18 @@ def main():
     report("advection 40x36, 10 steps", full, ref_uh)
     ctx.close()
 
+    # Euler system (4 components, halo width 4)
+    from oracle import euler as E
+
+    x, c = meshes.rectangle(40, 20, (0, 0), (2, 1))
+    ctx = Context((x, c), device=local, comm=comm)
+    dt = 0.2 * 2 / 40
+    U = GS.solve_euler(ctx, dt=dt, num_steps=6)
+    full = np.stack([D.allgather_field(ctx, np.ascontiguousarray(U[:, k]), dist) for k in range(4)], axis=1)
+    ref, _ = E.run_euler(x, c, dt, 6)
+    report("euler 40x20 sod, 6 steps", full, ref["Uh"])
+    ctx.close()
+
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
