@@ -150,6 +150,8 @@ struct cfem_ctx {
   double *stage[4] = {nullptr};   // staging for host<->device + permutation
   double *partials = nullptr;     // 8 * kMaxPartials doubles
   double *partials12 = nullptr;   // 12 more slots (Euler: sum/min/max of 4 components)
+  double* gmres_V = nullptr;      // lazily allocated Krylov basis (31 vectors) and small dense block
+  double* gmres_small = nullptr;
   void* euler = nullptr;          // lazily created Euler state (euler.cu)
   double *scalars = nullptr;      // small device scalar block
   int32_t* status = nullptr;      // device ints: [0]=done flag, [1]=iterations

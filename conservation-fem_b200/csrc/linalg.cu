@@ -871,8 +871,246 @@ SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, d
   return bicgstab_generic(c, c->dm.no, 1, A.dinv, op, c->wk, b, x, rtol, atol, max_it, predict);
 }
 
-SolveResult gmres(cfem_ctx*, const Matrix&, const double*, double*, double, double, int, int*) {
-  CFEM_THROW(-4, "GMRES is not built yet; use CFEM_SOLVER_BICGSTAB");
+// ---------------------------------------------------------------- restarted GMRES(30), right Jacobi
+// Arnoldi with classical Gram-Schmidt (all inner products of a step in one pass over the basis), Givens
+// rotations and the small triangular solve on the device; the host only polls the done flag.
+//   per step:  w = A (D^-1 v_j) ; h_i = (w, v_i), i <= j ; w -= sum h_i v_i ; v_{j+1} = w / ||w||
+constexpr int kGmresM = 30;
+// layout of the small device block (doubles): H (31 x 30, column major) | cs[30] | sn[30] | g[31] | y[30] | misc
+constexpr int kGmH = 0, kGmCs = 31 * 30, kGmSn = kGmCs + 30, kGmG = kGmSn + 30, kGmY = kGmG + 31, kGmMisc = kGmY + 30,
+              kGmSmall = kGmMisc + 8;
+
+__global__ void __launch_bounds__(kBlock)
+k_gm_residual(int64_t n, const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ w,
+              double* __restrict__ part_rr, double* __restrict__ part_bb) {
+  __shared__ double red[9];
+  double rr = 0.0, bb = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const double bi = b[i], ri = bi - q[i];
+    w[i] = ri;
+    rr += ri * ri; bb += bi * bi;
+  }
+  rr = block_sum(rr, red); bb = block_sum(bb, red);
+  if (threadIdx.x == 0) { part_rr[blockIdx.x] = rr; part_bb[blockIdx.x] = bb; }
+}
+
+// start of a cycle: beta = ||r||, g = beta e_1, convergence test on the TRUE residual
+__global__ void k_gm_start(const double* __restrict__ part_rr, const double* __restrict__ part_bb, int npart,
+                           double* __restrict__ sm, double* __restrict__ scalars, int32_t* __restrict__ status,
+                           double rtol2, double atol2, int first_cycle) {
+  __shared__ double red[9];
+  const double rr = reduce_partials(part_rr, npart, red);
+  const double bbn = reduce_partials(part_bb, npart, red);
+  if (threadIdx.x == 0) {
+    if (first_cycle) { scalars[S_BB] = bbn; status[1] = 0; }
+    const double bb = first_cycle ? bbn : scalars[S_BB];
+    scalars[S_RR] = rr;
+    scalars[S_RELRES] = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
+    sm[kGmG] = sqrt(rr);
+    sm[kGmMisc] = 0.0;      // Arnoldi steps completed in this cycle
+    sm[kGmMisc + 1] = sqrt(rr);  // norm used to normalise v_0
+    status[0] = !(rr == rr) ? 2 : ((rr <= rtol2 * bb || rr <= atol2) ? 1 : 0);
+  }
+}
+
+// v = w / nrm ; z = D^-1 v     (nrm read from the small block: slot kGmMisc+1)
+__global__ void __launch_bounds__(kBlock)
+k_gm_normalize(int64_t n, const double* __restrict__ w, const double* __restrict__ dinv, const double* __restrict__ sm,
+               double* __restrict__ v, double* __restrict__ z, const int32_t* __restrict__ status) {
+  if (status[0]) return;
+  const double inv = 1.0 / sm[kGmMisc + 1];
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const double vi = w[i] * inv;
+    v[i] = vi; z[i] = dinv[i] * vi;
+  }
+}
+
+// partial (w, v_i) for i = 0..j: one pass over w and the basis
+__global__ void __launch_bounds__(kBlock)
+k_gm_dots(int64_t n, int64_t stride, int j, const double* __restrict__ w, const double* __restrict__ V,
+          double* __restrict__ gp, const int32_t* __restrict__ status) {
+  if (status[0]) return;
+  __shared__ double red[9];
+  double acc[kGmresM + 1];
+#pragma unroll
+  for (int i = 0; i <= kGmresM; ++i) acc[i] = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)kBlock + threadIdx.x; e < n; e += (int64_t)gridDim.x * kBlock) {
+    const double we = w[e];
+#pragma unroll
+    for (int i = 0; i <= kGmresM; ++i)
+      if (i <= j) acc[i] += we * V[(size_t)i * stride + e];
+  }
+#pragma unroll
+  for (int i = 0; i <= kGmresM; ++i)
+    if (i <= j) {
+      const double a = block_sum(acc[i], red);
+      if (threadIdx.x == 0) gp[(size_t)i * kMaxPartials + blockIdx.x] = a;
+    }
+}
+
+// slot[k][0] = sum of its partials (one CTA per slot) — single-GPU counterpart of allreduce_partials
+__global__ void __launch_bounds__(kBlock)
+k_gm_reduce(double* __restrict__ gp, int npart) {
+  __shared__ double red[9];
+  double* p = gp + (size_t)blockIdx.x * kMaxPartials;
+  const double s = reduce_partials(p, npart, red);
+  if (threadIdx.x == 0) p[0] = s;
+}
+
+// w -= sum_i h_i v_i (h_i = gp[i][0]) ; partial ||w||^2 -> gp[m+1]
+__global__ void __launch_bounds__(kBlock)
+k_gm_update(int64_t n, int64_t stride, int j, double* __restrict__ w, const double* __restrict__ V,
+            double* __restrict__ gp, double* __restrict__ sm, const int32_t* __restrict__ status) {
+  if (status[0]) return;
+  __shared__ double red[9];
+  __shared__ double h[kGmresM + 1];
+  if (threadIdx.x <= j) h[threadIdx.x] = gp[(size_t)threadIdx.x * kMaxPartials];
+  __syncthreads();
+  double nn = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)kBlock + threadIdx.x; e < n; e += (int64_t)gridDim.x * kBlock) {
+    double we = w[e];
+    for (int i = 0; i <= j; ++i) we -= h[i] * V[(size_t)i * stride + e];
+    w[e] = we;
+    nn += we * we;
+  }
+  nn = block_sum(nn, red);
+  if (threadIdx.x == 0) gp[(size_t)(kGmresM + 1) * kMaxPartials + blockIdx.x] = nn;
+  if (blockIdx.x == 0 && threadIdx.x <= j) sm[kGmH + j * (kGmresM + 1) + threadIdx.x] = h[threadIdx.x];
+}
+
+// column j of the Hessenberg matrix: previous rotations, new rotation, residual estimate |g_{j+1}|
+__global__ void k_gm_givens(int j, const double* __restrict__ gp, int npart, double* __restrict__ sm,
+                            double* __restrict__ scalars, int32_t* __restrict__ status, double rtol2, double atol2) {
+  __shared__ double red[9];
+  if (status[0]) return;
+  const double nn = reduce_partials(gp + (size_t)(kGmresM + 1) * kMaxPartials, npart, red);
+  if (threadIdx.x == 0) {
+    double* H = sm + kGmH + j * (kGmresM + 1);
+    double *cs = sm + kGmCs, *sn = sm + kGmSn, *g = sm + kGmG;
+    const double hn = sqrt(nn);
+    H[j + 1] = hn;
+    sm[kGmMisc + 1] = hn;  // normalises v_{j+1}
+    for (int i = 0; i < j; ++i) {
+      const double t = cs[i] * H[i] + sn[i] * H[i + 1];
+      H[i + 1] = -sn[i] * H[i] + cs[i] * H[i + 1];
+      H[i] = t;
+    }
+    const double d = sqrt(H[j] * H[j] + hn * hn);
+    cs[j] = d > 0.0 ? H[j] / d : 1.0;
+    sn[j] = d > 0.0 ? hn / d : 0.0;
+    H[j] = d;
+    H[j + 1] = 0.0;
+    g[j + 1] = -sn[j] * g[j];
+    g[j] = cs[j] * g[j];
+    sm[kGmMisc] = (double)(j + 1);
+    status[1] += 1;
+    const double res = g[j + 1] * g[j + 1], bb = scalars[S_BB];
+    scalars[S_RR] = res;
+    scalars[S_RELRES] = bb > 0.0 ? sqrt(res / bb) : sqrt(res);
+    if (!(res == res)) status[0] = 2;
+    else if (res <= 0.25 * rtol2 * bb || res <= 0.25 * atol2 || hn == 0.0) status[0] = 3;  // cycle ends: verify on the true residual
+  }
+}
+
+// y = H^-1 g (k x k upper triangular, k = steps completed in this cycle)
+__global__ void k_gm_solve(double* __restrict__ sm) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int k = (int)sm[kGmMisc];
+  double* y = sm + kGmY;
+  for (int i = k - 1; i >= 0; --i) {
+    double s = sm[kGmG + i];
+    for (int l = i + 1; l < k; ++l) s -= sm[kGmH + l * (kGmresM + 1) + i] * y[l];
+    y[i] = s / sm[kGmH + i * (kGmresM + 1) + i];
+  }
+}
+
+// x += D^-1 sum_i y_i v_i
+__global__ void __launch_bounds__(kBlock)
+k_gm_xupdate(int64_t n, int64_t stride, const double* __restrict__ V, const double* __restrict__ dinv,
+             const double* __restrict__ sm, double* __restrict__ x) {
+  __shared__ double y[kGmresM];
+  const int k = (int)sm[kGmMisc];
+  if (threadIdx.x < k) y[threadIdx.x] = sm[kGmY + threadIdx.x];
+  __syncthreads();
+  for (int64_t e = blockIdx.x * (int64_t)kBlock + threadIdx.x; e < n; e += (int64_t)gridDim.x * kBlock) {
+    double s = 0.0;
+    for (int i = 0; i < k; ++i) s += y[i] * V[(size_t)i * stride + e];
+    x[e] += dinv[e] * s;
+  }
+}
+
+SolveResult gmres(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol, int max_it,
+                  int* predict) {
+  const int64_t n = c->dm.no, nl = c->dm.nn;
+  if (!c->gmres_V) {
+    void* p = nullptr;
+    CUDA_OK(cudaMalloc(&p, (size_t)(kGmresM + 1) * nl * sizeof(double)));
+    c->allocs.push_back(p);
+    c->bytes += (int64_t)(kGmresM + 1) * nl * sizeof(double);
+    c->gmres_V = (double*)p;
+    CUDA_OK(cudaMalloc(&p, ((size_t)(kGmresM + 2) * kMaxPartials + kGmSmall) * sizeof(double)));
+    c->allocs.push_back(p);
+    c->gmres_small = (double*)p;
+  }
+  double* V = c->gmres_V;
+  double* gp = c->gmres_small;                                       // (m+2) partial arrays
+  double* sm = c->gmres_small + (size_t)(kGmresM + 2) * kMaxPartials;  // small dense block
+  double *w = c->wk[0], *z = c->wk[1], *q = c->wk[2];
+  double* part = c->partials;
+  const int gv = vec_grid(c, n);
+  const double rtol2 = rtol * rtol, atol2 = atol * atol;
+  const bool dist = c->world > 1;
+  SolveResult res{0, 0.0, false};
+  int total = 0;
+  int next_poll = predict && *predict > 1 ? *predict : 8;
+  for (int cycle = 0;; ++cycle) {
+    // true residual r = b - A x: starts a cycle and is the convergence verdict on the previous one
+    launch_spmv(c, A, x, q);
+    { ProfScope ps(c, PROF_KRYLOV_VEC);
+      k_gm_residual<<<gv, kBlock, 0, c->stream>>>(n, b, q, w, part + P_RR * kMaxPartials, part + P_BB * kMaxPartials); LAUNCHED(c); }
+    int np = gv;
+    if (dist) { double* sl[2] = {part + P_RR * kMaxPartials, part + P_BB * kMaxPartials}; const int op[2] = {0, 0}; np = allreduce_partials(c, 2, sl, op, gv); }
+    { ProfScope ps(c, PROF_KRYLOV_VEC);
+      k_gm_start<<<1, kBlock, 0, c->stream>>>(part + P_RR * kMaxPartials, part + P_BB * kMaxPartials, np, sm, c->scalars, c->status, rtol2, atol2, cycle == 0); LAUNCHED(c); }
+    if (cycle > 0 || total >= max_it) {  // the first cycle defers this poll to the inner loop (x0 is rarely converged)
+      if (poll_done(c, res) || total >= max_it) break;
+    }
+    { ProfScope ps(c, PROF_KRYLOV_VEC); k_gm_normalize<<<gv, kBlock, 0, c->stream>>>(n, w, A.dinv, sm, V, z, c->status); LAUNCHED(c); }
+    for (int j = 0; j < kGmresM && total < max_it; ++j) {
+      spmv_dots<0>(c, A, z, w, nullptr, nullptr, nullptr, nullptr, true);
+      { ProfScope ps(c, PROF_KRYLOV_VEC); k_gm_dots<<<gv, kBlock, 0, c->stream>>>(n, nl, j, w, V, gp, c->status); LAUNCHED(c); }
+      if (dist) {
+        for (int i0 = 0; i0 <= j; i0 += 8) {
+          double* sl[8]; const int op[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          const int cnt = std::min(8, j + 1 - i0);
+          for (int k = 0; k < cnt; ++k) sl[k] = gp + (size_t)(i0 + k) * kMaxPartials;
+          allreduce_partials(c, cnt, sl, op, gv);
+        }
+      } else {
+        ProfScope ps(c, PROF_KRYLOV_VEC); k_gm_reduce<<<j + 1, kBlock, 0, c->stream>>>(gp, gv); LAUNCHED(c);
+      }
+      { ProfScope ps(c, PROF_KRYLOV_VEC); k_gm_update<<<gv, kBlock, 0, c->stream>>>(n, nl, j, w, V, gp, sm, c->status); LAUNCHED(c); }
+      const int npn = allreduce_sum1(c, gp + (size_t)(kGmresM + 1) * kMaxPartials, gv);
+      { ProfScope ps(c, PROF_KRYLOV_VEC);
+        k_gm_givens<<<1, kBlock, 0, c->stream>>>(j, gp, npn, sm, c->scalars, c->status, rtol2, atol2); LAUNCHED(c);
+        k_gm_normalize<<<gv, kBlock, 0, c->stream>>>(n, w, A.dinv, sm, V + (size_t)(j + 1) * nl, z, c->status); LAUNCHED(c); }
+      ++total;
+      if (total >= next_poll || total == max_it) {
+        CUDA_OK(cudaMemcpyAsync(c->h_status, c->status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (c->h_status[0] != 0) break;  // estimate met the tolerance (3), or NaN (2): close the cycle
+        next_poll = total + 2;
+      }
+    }
+    // close the cycle: x += D^-1 V y (k_gm_solve uses the number of steps the device actually completed)
+    { ProfScope ps(c, PROF_KRYLOV_VEC);
+      k_gm_solve<<<1, 32, 0, c->stream>>>(sm); LAUNCHED(c);
+      k_gm_xupdate<<<gv, kBlock, 0, c->stream>>>(n, nl, V, A.dinv, sm, x); LAUNCHED(c); }
+  }
+  if (!res.converged) poll_done(c, res);
+  halo_exchange(c, x);
+  if (predict) *predict = res.iters > 0 ? res.iters : 1;
+  return res;
 }
 
 }  // namespace cfem

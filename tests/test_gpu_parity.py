@@ -177,7 +177,7 @@ def test_advection_system(case):
         assert abs(Ag - Ar).max() <= 1e-13 * abs(Ar).max()
 
 
-@pytest.mark.parametrize("solver", ["pcg", "chebyshev", "bicgstab"])
+@pytest.mark.parametrize("solver", ["pcg", "chebyshev", "bicgstab", "gmres"])
 def test_krylov_vs_lu(case, solver):
     from scipy.sparse.linalg import splu
 
@@ -230,11 +230,12 @@ def test_device_pointer_arguments(case):
 TOL_FIELD = 1e-10  # north-star tolerance: relative L2 after N steps
 
 
-def test_burgers_steps():
+@pytest.mark.parametrize("solver", ["bicgstab", "gmres"])
+def test_burgers_steps(solver):
     x, c = meshes.rectangle(48, 48)
     dt, n = 0.5 / 48, 12
     st, m, h = S.run_burgers(x, c, dt, n)
-    uh, stats = GS.solve_burgers((x, c), dt=dt, num_steps=n, return_stats=True)
+    uh, stats = GS.solve_burgers((x, c), dt=dt, num_steps=n, solver=solver, return_stats=True)
     assert rel(uh.x.array, st.uh) < TOL_FIELD
     assert stats["newton_iterations"] == sum(st.newton_its)
     assert rel(stats["eps"], st.eps) < 1e-8
