@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libcfem_b200.so")
 # enums (mirror include/cfem_b200.h)
 FLUX_ADVECTION, FLUX_BURGERS, FLUX_KPP = 0, 1, 2
 BDF1, BDF2 = 1, 2
-EPS_NONLINEAR, EPS_LINEAR, EPS_POINTWISE, EPS_FIRST_ORDER, EPS_LINEAR_SIMPLE = 0, 1, 2, 3, 4
+EPS_NONLINEAR, EPS_LINEAR, EPS_POINTWISE, EPS_FIRST_ORDER, EPS_LINEAR_SIMPLE, EPS_CELL = 0, 1, 2, 3, 4, 5
 MAT_MASS, MAT_MASS_BC, MAT_SYSTEM, MAT_STIFFNESS = 0, 1, 2, 3
 SOLVER_PCG, SOLVER_BICGSTAB, SOLVER_GMRES, SOLVER_CHEBYSHEV = 0, 1, 2, 3
 BC_CONSTANT, BC_BURGERS_EXACT, BC_USER = 0, 1, 2
@@ -119,7 +119,7 @@ SIGNATURES = {
 
 HM_ARRAYS = {"n2u": 0, "cells": 1, "rowptr": 2, "colidx": 3, "v2c_ptr": 4, "v2c_code": 5, "tile_node": 6,
              "tile_cellptr": 7, "tile_cells": 8, "is_bnd": 9, "bnd_user": 10, "peer_rank": 11, "send_ptr": 12,
-             "send_idx": 13, "recv_off": 14, "recv_cnt": 15}
+             "send_idx": 13, "recv_off": 14, "recv_cnt": 15, "last_cell": 16}
 
 
 def host_analyse(x, cells, order=ORDER_HILBERT, rank=0, world=1):

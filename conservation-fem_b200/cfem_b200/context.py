@@ -151,7 +151,8 @@ class Context:
     # -- (a-4..6)
     def rv_epsilon(self, variant, flux, Cvel, Crv, uh=None, u_n=None, Rh=None, h=None, w=None, out=None):
         variant = {"nonlinear": L.EPS_NONLINEAR, "linear": L.EPS_LINEAR, "pointwise": L.EPS_POINTWISE,
-                   "first_order": L.EPS_FIRST_ORDER, "linear_simple": L.EPS_LINEAR_SIMPLE}.get(variant, variant)
+                   "first_order": L.EPS_FIRST_ORDER, "linear_simple": L.EPS_LINEAR_SIMPLE,
+                   "cell": L.EPS_CELL}.get(variant, variant)
         eps = np.empty(self.n) if out is None else out
         uh, u_n, Rh, h, w = _field(uh), _field(u_n), _field(Rh), _field(h), _field(w)
         L.check(self._lib.cfem_rv_epsilon(self._h, variant, _flux(flux), float(Cvel), float(Crv), L.ptr(uh),

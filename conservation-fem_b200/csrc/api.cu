@@ -264,6 +264,7 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   dm.tile_cells = upload(c, hm.tile_cells);
   dm.tile_order = upload(c, hm.tile_order);
   dm.n_interior = hm.n_interior_tiles;
+  dm.last_cell = upload(c, hm.last_cell);
   c->d_n2u = upload(c, hm.n2u);
   c->d_u2n = world == 1 ? upload(c, hm.u2n) : nullptr;  // user -> local is only a permutation on one GPU
   c->d_send_idx = upload(c, hm.send_idx);
@@ -967,6 +968,7 @@ static auto host_array(const cfem_host_mesh* h, int what, F&& f) {
     case CFEM_HM_SEND_IDX: return f(m.send_idx.data(), m.send_idx.size(), 4);
     case CFEM_HM_RECV_OFF: return f(m.recv_off.data(), m.recv_off.size(), 4);
     case CFEM_HM_RECV_CNT: return f(m.recv_cnt.data(), m.recv_cnt.size(), 4);
+    case CFEM_HM_LAST_CELL: return f(m.last_cell.data(), m.last_cell.size(), 4);
     default: return f(nullptr, (size_t)0, 0);
   }
 }

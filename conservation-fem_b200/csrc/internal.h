@@ -59,6 +59,7 @@ struct HostMesh {
   std::vector<int32_t> tile_order;        // tiles whose rows touch no ghost column first, the others last
   int n_interior_tiles = 0;
   std::vector<uint8_t> is_bnd;            // nn
+  std::vector<int32_t> last_cell;         // n_owned: incident local cell with the highest caller index
   std::vector<int32_t> bnd_user_sorted;   // boundary dofs, user ids ascending
   int max_row = 0, max_tile_cells = 0, max_tile_nnz = 0;
 };
@@ -86,6 +87,7 @@ struct DevMesh {
   const int32_t* tile_order;   // interior tiles first (identity on one GPU)
   int n_interior;              // number of tiles that need no ghost value
   const uint8_t* is_bc;    // current Dirichlet flags
+  const int32_t* last_cell;  // per owned node, see HostMesh
 };
 
 constexpr int kMaxPartials = 4096;   // >= any reduction grid

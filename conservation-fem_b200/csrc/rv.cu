@@ -148,6 +148,47 @@ k_epsilon_pointwise(int64_t n, int64_t n_global, int variant, const double* __re
   }
 }
 
+// Cell-based viscosity of Code/Linear_advection/RV_cell.py:174-192: the residual is divided by
+// max(u_n - mean(u_n)), every cell gets min(Cvel h_K max|w|, Crv h_K^2 max|R|) over its three dofs with
+// h_K its shortest edge, and the per-cell loop writes that value to the three dofs in cell order -- so a
+// node ends up with the value of its highest-numbered cell (last_cell).  One thread per owned node.
+__global__ void __launch_bounds__(kBlock)
+k_epsilon_cell(int64_t n_owned, int64_t n_global, const int32_t* __restrict__ cells,
+               const int32_t* __restrict__ last_cell, const double2* __restrict__ xy,
+               const double* __restrict__ Rh, const double2* __restrict__ w, const double* __restrict__ part,
+               int npart, double Cvel, double Crv, double* __restrict__ eps) {
+  __shared__ double red[9];
+  double s = 0.0, mx = -INFINITY;
+  for (int i = threadIdx.x; i < npart; i += kBlock) {
+    s += part[P_SUM * kMaxPartials + i];
+    mx = fmax(mx, part[P_MAX * kMaxPartials + i]);
+  }
+  s = block_sum(s, red); mx = block_max(mx, red);
+  const double A = mx - s / (double)n_global;   // np.max(u_n - np.mean(u_n))
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n_owned; i += (int64_t)gridDim.x * kBlock) {
+    const int64_t c = last_cell[i];
+    double2 p[3];
+    double Rk = 0.0, Bk = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int32_t v = cells[3 * c + k];
+      p[k] = xy[v];
+      const double2 wv = w[v];
+      Rk = fmax(Rk, fabs(Rh[v] / A));
+      Bk = fmax(Bk, sqrt(__dadd_rn(__dmul_rn(wv.x, wv.x), __dmul_rn(wv.y, wv.y))));
+    }
+    double hk = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = a + 1; b < 3; ++b) {
+        const double dx = p[a].x - p[b].x, dy = p[a].y - p[b].y;
+        hk = fmin(hk, sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+      }
+    eps[i] = pymin(__dmul_rn(__dmul_rn(Cvel, hk), Bk), __dmul_rn(__dmul_rn(Crv, __dmul_rn(hk, hk)), Rk));
+  }
+}
+
 // all-reduce the sum / min / max partials over the ranks; returns the partial count to use
 static int stats_allreduce(cfem_ctx* c, int gv) {
   double* sl[3] = {c->partials + P_SUM * kMaxPartials, c->partials + P_MIN * kMaxPartials, c->partials + P_MAX * kMaxPartials};
@@ -167,6 +208,16 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
   const int64_t n = c->dm.no, nl = c->dm.nn, ng = c->dm.nn_global;
   const int gv = vec_grid(c, nl);
   int np = gv;
+  if (variant == CFEM_EPS_CELL) {
+    if (!u_n || !Rh || !w) CFEM_THROW(-1, "rv_epsilon(cell): u_n, Rh and w are required");
+    k_stats<-1><<<gv, kBlock, 0, c->stream>>>(n, nl, u_n, nullptr, c->partials); LAUNCHED(c);
+    np = stats_allreduce(c, gv);
+    k_epsilon_cell<<<vec_grid(c, n), kBlock, 0, c->stream>>>(n, ng, c->dm.cells, c->dm.last_cell, c->dm.xy, Rh, w,
+                                                            c->partials, np, Cvel, Crv, eps);
+    LAUNCHED(c);
+    halo_exchange(c, eps);
+    return;
+  }
   if (!h) CFEM_THROW(-1, "rv_epsilon: nodal mesh size h is required");
   if (variant == CFEM_EPS_NONLINEAR || variant == CFEM_EPS_LINEAR) {
     if (!uh || !u_n || !Rh) CFEM_THROW(-1, "rv_epsilon: uh, u_n and Rh are required");

@@ -46,6 +46,7 @@ struct GlobalMesh {
   std::vector<int32_t> n2u, u2n;
   std::vector<double> xy;
   std::vector<int32_t> cells;    // 3*nc, sorted by smallest vertex
+  std::vector<int32_t> cell_user;  // nc, the caller's index of each sorted cell
   std::vector<int32_t> v2c_ptr;  // nn+1
   std::vector<int32_t> v2c;      // 3*nc  cell of each (vertex, incident cell) pair, ascending
   std::vector<uint8_t> v2k;      // 3*nc  local vertex number in that cell
@@ -119,6 +120,7 @@ static void global_analysis(GlobalMesh& g, int64_t nn, int64_t nc, const double*
     if (rep_bad) CFEM_THROW(-1, "cell connectivity has a repeated vertex");
   }
   g.cells.resize(3 * nc);
+  g.cell_user.resize(nc);
   {
     std::vector<int32_t> cnt(nn + 1, 0);  // counting sort by min vertex (stable -> deterministic)
     for (int64_t c = 0; c < nc; ++c)
@@ -130,6 +132,7 @@ static void global_analysis(GlobalMesh& g, int64_t nn, int64_t nc, const double*
       g.cells[3 * p] = ctmp[3 * c];
       g.cells[3 * p + 1] = ctmp[3 * c + 1];
       g.cells[3 * p + 2] = ctmp[3 * c + 2];
+      g.cell_user[p] = (int32_t)c;
     }
   }
   std::vector<int32_t>().swap(ctmp);
@@ -296,6 +299,18 @@ static void build_local(const GlobalMesh& g, int rank, int world, HostMesh& hm, 
       lv2c[e] = (int32_t)(std::lower_bound(lcells.begin(), lcells.end(), gc) - lcells.begin());
       lv2k[e] = g.v2k[g.v2c_ptr[lo] + e];
     }
+  }
+  // per owned node the incident cell with the highest caller index: a per-cell loop that writes a cell
+  // value to its three dofs (Code/Linear_advection/RV_cell.py:190-192) leaves exactly that cell's value
+  hm.last_cell.resize(no);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < no; ++i) {
+    int32_t best = -1, best_user = -1;
+    for (int e = hm.v2c_ptr[i]; e < hm.v2c_ptr[i + 1]; ++e) {
+      const int32_t cu = g.cell_user[g.v2c[g.v2c_ptr[lo] + e]];
+      if (cu > best_user) { best_user = cu; best = lv2c[e]; }
+    }
+    hm.last_cell[i] = best;
   }
 
   // boundary dofs in caller numbering: global list (every rank reports the same set)

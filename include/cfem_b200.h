@@ -37,7 +37,8 @@ enum { CFEM_EPS_NONLINEAR = 0,     /* RV.get_epsilon_nonlinear   RV.py:56-90   *
        CFEM_EPS_LINEAR = 1,        /* RV.get_epsilon_linear      RV.py:92-127  */
        CFEM_EPS_POINTWISE = 2,     /* RV.get_epsilon             RV.py:27-40   */
        CFEM_EPS_FIRST_ORDER = 3,   /* RV.get_epsilon_1storder    RV.py:42-54   */
-       CFEM_EPS_LINEAR_SIMPLE = 4  /* RV.get_epsilon_linear_simple RV.py:129-142 */ };
+       CFEM_EPS_LINEAR_SIMPLE = 4, /* RV.get_epsilon_linear_simple RV.py:129-142 */
+       CFEM_EPS_CELL = 5           /* per-cell loop of Code/Linear_advection/RV_cell.py:174-192 (needs u_n, Rh, w; h unused) */ };
 enum { CFEM_MAT_MASS = 0,          /* int u v, no Dirichlet rows              */
        CFEM_MAT_MASS_BC = 1,       /* same, Dirichlet rows/cols -> identity   */
        CFEM_MAT_SYSTEM = 2,        /* last assembled CN matrix / Jacobian     */
@@ -264,7 +265,8 @@ enum { CFEM_HM_N2U = 0, CFEM_HM_CELLS = 1, CFEM_HM_ROWPTR = 2, CFEM_HM_COLIDX = 
        CFEM_HM_IS_BND = 9 /* uint8 */, CFEM_HM_BND_USER = 10,
        /* partition (cfem_host_analyse_part): peers and halo lists of this rank */
        CFEM_HM_PEER_RANK = 11, CFEM_HM_SEND_PTR = 12, CFEM_HM_SEND_IDX = 13, CFEM_HM_RECV_OFF = 14,
-       CFEM_HM_RECV_CNT = 15 };
+       CFEM_HM_RECV_CNT = 15,
+       CFEM_HM_LAST_CELL = 16 /* per owned node: incident local cell with the highest caller index */ };
 int cfem_host_analyse(cfem_host_mesh** out, int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
                       const void* cells, int cell_index_bytes, int order);
 /* same, restricted to rank's part of a world-way partition (what cfem_create_distributed builds) */

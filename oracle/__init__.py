@@ -22,15 +22,29 @@ and 7-point degree-5 symmetric triangle rules, dolfinx's Dirichlet lifting
 convention and NewtonSolver stopping rules, and a sparse direct LU
 (``scipy.sparse.linalg.splu``) standing in for ``KSP preonly + PC lu``.
 
-PARITY UNPINNED against dolfinx itself: the reference holds no assertion, no
-golden vector and no known-answer test for this path.
-What *is* pinned, in ``tests/test_oracle_*.py``:
+PINNED against dolfinx itself for the linear path, UNPINNED for the nonlinear one.
+
+The reference holds no assertion and no known-answer test for this path, but
+it does store dolfinx output: three 285-frame time series on its 1,011-node unit-disk mesh,
+``Code/Linear_advection/Data/RV/RV_node.h5`` (written by ``tests/eps_func.py``),
+``Data/RV/RV_cell.h5`` (``RV_cell.py``) and ``Data/SI/smoothness.h5`` (the loop of
+``smoothness_old_convergence.py``).  ``solvers.run_advection_stored`` restates those three scripts and
+reproduces every one of the 3 x 285 stored frames to <= 1.2e-14 relative L2
+(``tests/golden/make_golden.py`` checks all frames, ``tests/test_oracle_pinned.py`` the 13 committed
+per series).  That pins, against dolfinx 0.9 / PETSc LU: P1 mass, convection and nodal-viscosity
+stiffness assembly, the Dirichlet rows and lifting, the L2 projection of h_K, the BDF1 residual
+projection and its normalisation, the pointwise and cell-based viscosities, the smoothness ratio,
+every entry of the assembled Crank-Nicolson matrix (the si_old run feeds them back into alpha), and
+the ``dt`` formula / time stamps.
+
+Still unpinned against dolfinx (no stored output exists: ``Code/Burgers_equation/Data/RV/solution.xdmf``
+has no ``.h5``, ``Data/KPP_RV.h5`` holds only a mesh, ``Data/RV/solution.h5`` is a P2 run): the
+nonlinear flux quadrature (6-/7-point rules), the Newton loop and the patch-based ``RV.py`` formulas.
+Those rest on:
 
 * analytic known answers on the reference's ``tests/verification`` meshes
   (``hk_test.py:36-38``, ``stiffness.py:38``, ``patch_test.py:15``);
-* P1 identities (row sums of M, C·1 = 0, K·1 = 0, quadrature exactness);
-* the first time stamp of ``Code/Linear_advection/Data/RV/RV_node.xdmf``
-  (``dt`` formula, 16 digits) on the mesh stored in ``RV_node.h5``;
+* P1 identities (row sums of M, C.1 = 0, K.1 = 0, quadrature exactness, J = dF/du);
 * the literal per-node Python loops of ``RV.py`` against the vectorised forms;
 * observed convergence rates against the published ones.
 """

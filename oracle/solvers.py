@@ -398,3 +398,89 @@ def l2_error_nodal(m: Mesh, uh, u_ref):
     """sqrt(int (uh - I_h u_ref)^2) with both fields P1 (mass-matrix norm)."""
     d = uh - u_ref
     return float(np.sqrt(d @ (m.M @ d)))
+
+
+# ------------------------------------------------------------------ the reference's stored dolfinx series
+# Restatements of the three scripts whose XDMF/HDF5 output the reference keeps under
+# ``Code/Linear_advection/Data`` (unit disk, gmsh h = 1/16, 1,011 nodes, 285 frames each).  They differ
+# from ``run_advection`` only in how the nodal viscosity is formed; the tests compare every stored frame
+# with these (``tests/test_oracle_pinned.py``) -- this is what pins the oracle against dolfinx itself.
+
+
+def discontinuous_cylinder(x, r0=0.25, x0_1=0.3, x0_2=0.0):
+    """``tests/eps_func.py:44-45`` (also ``RV_cell.py:44-45``, ``smoothness.py`` "Discont. IC")."""
+    x = np.asarray(x, dtype=np.float64)
+    return ((x[:, 0] - x0_1) ** 2 + (x[:, 1] - x0_2) ** 2 <= r0 ** 2).astype(np.float64)
+
+
+def si_alpha(Kw, u, floor=1e-8):
+    """alpha_i = |sum_j k_ij (u_j - u_i)| / max(sum_j |k_ij| |u_j - u_i|, floor) with the weights k_ij
+    read from the CSR matrix ``Kw`` (``smoothness_old_convergence.py:228-246``, ``SI.py:160-185``)."""
+    Kw = Kw.tocsr()
+    Kw.sort_indices()
+    n = Kw.shape[0]
+    rows = np.repeat(np.arange(n), np.diff(Kw.indptr))
+    du = u[Kw.indices] - u[rows]
+    num = np.zeros(n)
+    den = np.zeros(n)
+    np.add.at(num, rows, Kw.data * du)
+    np.add.at(den, rows, np.abs(Kw.data) * np.abs(du))
+    return np.abs(num) / np.maximum(den, floor)
+
+
+def run_advection_stored(x, cells, variant, num_steps=None, hmax=1 / 16, Cvel=0.25, Crv=1.0, Cm=0.05):
+    """All frames ``uh(t_k)``, k = 1..num_steps, of one of the stored runs.
+
+    variant
+      ``"eps_func"``  ``tests/eps_func.py:166-249`` -> ``Data/RV/RV_node.h5``: one GFEM step, then BDF1
+                      residual projected *without* bc, divided by ``max(u_n - mean u_n)``, pointwise
+                      ``min(Cvel h |w|, Crv h^2 |R|)``.
+      ``"rv_cell"``   ``Code/Linear_advection/RV_cell.py:166-231`` -> ``Data/RV/RV_cell.h5``: same residual
+                      (the stored run predates the ``bcs=[bc]`` in line 173); per cell
+                      ``min(Cvel h_K max|w|, Crv h_K^2 max|R|)`` written to the cell's three dofs in cell
+                      order, so each node keeps the value of its highest-numbered cell.
+      ``"si_old"``    ``smoothness_old_convergence.py:184-253`` -> ``Data/SI/smoothness.h5``:
+                      ``eps = alpha Cm h |w|`` with no activation, Cm = 0.05; the script rebinds the name
+                      ``A`` from the bc'd unit stiffness matrix to the step's system matrix (line 181 vs
+                      the loop body), so from the second SI step on the weights ``A.getValue(i, j)`` are
+                      the previous step's Crank-Nicolson matrix.  Restated as run.
+    """
+    x = np.asarray(x, dtype=np.float64)
+    m = Mesh(x, cells)
+    w = advection_velocity(x)
+    wn = np.sqrt(w[:, 0] * w[:, 0] + w[:, 1] * w[:, 1])
+    dt = advection_dt(w, hmax)
+    num_steps = int(np.ceil(1.0 / dt)) if num_steps is None else num_steps
+    h = p1.nodal_h(m.x, m.cells)
+    hk = p1.min_edge(m.x, m.cells)
+    u_n = discontinuous_cylinder(x)
+    u_old = u_n.copy()
+    A, B = advection_system(m, dt, w)
+    uh = advection_solve(m, A, B, u_n)
+    u_n = uh.copy()
+    frames = [uh.copy()]
+    if variant == "si_old":
+        Kw = p1.apply_bc_matrix(p1.stiffness_matrix(m.x, m.cells), m.bnd)
+    for _ in range(num_steps - 1):
+        if variant == "si_old":
+            eps = si_alpha(Kw, u_n) * Cm * h * wn
+        else:
+            Rh = rv_residual("advection", m, dt, u_n, u_old, scheme="bdf1", bc=False, w=w)
+            Rh = Rh / np.max(u_n - np.mean(u_n))
+            if variant == "eps_func":
+                eps = rv.epsilon_pointwise(Cvel, Crv, wn, Rh, h)
+            elif variant == "rv_cell":
+                ek = np.minimum(Cvel * hk * wn[m.cells].max(axis=1), Crv * hk ** 2 * np.abs(Rh)[m.cells].max(axis=1))
+                eps = np.zeros(m.n)
+                for k in range(len(m.cells)):       # last writer wins (RV_cell.py:190-192)
+                    eps[m.cells[k]] = ek[k]
+            else:
+                raise ValueError(variant)
+        A, B = advection_system(m, dt, w, eps)
+        if variant == "si_old":
+            Kw = p1.apply_bc_matrix(A, m.bnd)
+        uh = advection_solve(m, A, B, u_n)
+        u_old = u_n.copy()
+        u_n = uh.copy()
+        frames.append(uh.copy())
+    return np.array(frames), m, dt

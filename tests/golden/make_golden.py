@@ -5,12 +5,19 @@
      Code/Linear_advection/Data/RV/RV_node.h5  -> rv_node_mesh.npz  (1,919 tris / 1,011 nodes, unit disk)
      Data/KPP_RV.h5                            -> kpp_rv_mesh.npz   (9,514 tris / 4,886 nodes, [-2,2]^2)
    plus the first <Time> stamp of RV_node.xdmf, which pins the reference's dt formula.
-2. Oracle outputs on small seeded cases (fields after N steps), so GPU parity can also be
-   checked against committed vectors.  These come from oracle/ (CPU restatement), not from
-   dolfinx: the reference cannot run in this image ("parity unpinned", see oracle/__init__.py).
+2. Frames of the three dolfinx time series the reference stores on that disk mesh
+     Code/Linear_advection/Data/RV/RV_node.h5   (tests/eps_func.py)                 -> ref_series_eps_func.npz
+     Code/Linear_advection/Data/RV/RV_cell.h5   (Code/Linear_advection/RV_cell.py)  -> ref_series_rv_cell.npz
+     Code/Linear_advection/Data/SI/smoothness.h5 (smoothness_old_convergence.py loop) -> ref_series_si_old.npz
+   (datasets located through their HDF5 data-layout messages; 13 of the 285 frames are kept, the
+   generator checks all 285 against the oracle).  These ARE dolfinx output: they pin the oracle.
+3. Oracle outputs on small seeded cases (fields after N steps), so GPU parity can also be
+   checked against committed vectors.  These come from oracle/ (CPU restatement): the reference
+   itself cannot run in this image (no dolfinx).
 """
 import os
 import re
+import struct
 import sys
 
 import numpy as np
@@ -32,6 +39,44 @@ def read_mesh(path, n_cells, n_nodes, topo_off, geom_off):
     return x.copy(), cells.astype(np.int32)
 
 
+def contiguous_datasets(raw, nbytes):
+    """File addresses of the contiguous HDF5 datasets of exactly ``nbytes`` (data layout message
+    version 3, class 1: ``03 01 <address:8> <size:8>``), in file (= creation = time) order."""
+    out = []
+    for mt in re.finditer(re.escape(struct.pack("<Q", nbytes)), raw):
+        p = mt.start()
+        a = struct.unpack("<Q", raw[p - 8:p])[0]
+        if raw[p - 10:p - 8] == b"\x03\x01" and 0 < a <= len(raw) - nbytes:
+            out.append(a)
+    return sorted(out)
+
+
+def read_series(path, n_nodes):
+    raw = open(path, "rb").read()
+    return np.array([np.frombuffer(raw, dtype="<f8", count=n_nodes, offset=a)
+                     for a in contiguous_datasets(raw, 8 * n_nodes)])
+
+
+KEEP = [0, 1, 2, 3, 5, 10, 20, 50, 100, 150, 200, 250, 284]
+SERIES = {"eps_func": "Code/Linear_advection/Data/RV/RV_node.h5",
+          "rv_cell": "Code/Linear_advection/Data/RV/RV_cell.h5",
+          "si_old": "Code/Linear_advection/Data/SI/smoothness.h5"}
+
+
+def stored_series(S, x, c):
+    for variant, rel in SERIES.items():
+        F = read_series(f"{REF}/{rel}", len(x))
+        xdmf = open(f"{REF}/{rel}".replace(".h5", ".xdmf")).read()
+        times = np.array([float(t) for t in re.findall(r'<Time Value="([0-9.eE+-]+)"', xdmf)])
+        assert F.shape == (285, len(x)) and len(times) == 285
+        U, _, dt = S.run_advection_stored(x, c, variant)
+        err = np.linalg.norm(U - F, axis=1) / np.linalg.norm(F, axis=1)
+        print(f"{variant}: oracle vs all 285 stored dolfinx frames, max rel L2 error {err.max():.2e}")
+        assert err.max() < 1e-12
+        np.savez_compressed(f"{HERE}/ref_series_{variant}.npz", frames=F[KEEP], index=np.array(KEEP),
+                            times=times[KEEP], dt=np.array(dt))
+
+
 def main():
     from oracle import p1, solvers as S
     from cfem_b200 import meshes
@@ -47,6 +92,8 @@ def main():
     area, _ = p1.cell_geometry(x, c)
     assert abs(area.sum() - 16.0) < 1e-9 and np.all(area > 0)
     np.savez_compressed(f"{HERE}/kpp_rv_mesh.npz", x=x, cells=c)
+    d = np.load(f"{HERE}/rv_node_mesh.npz")
+    stored_series(S, d["x"], d["cells"])
 
     # oracle outputs
     xb, cb = meshes.rectangle(24, 24)

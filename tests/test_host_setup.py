@@ -111,6 +111,24 @@ def test_host_analysis(name, order):
     assert abs(Mu - ref).max() <= 1e-15 * abs(ref).max()
 
 
+@pytest.mark.parametrize("world", [1, 3])
+def test_last_cell_is_highest_numbered_incident_cell(world):
+    """RV_cell.py:190-192 writes each cell's viscosity to its dofs in cell order: a node keeps the value
+    of its highest-numbered cell.  last_cell names that cell (by its vertex set; cells are renumbered)."""
+    x, c = meshes.permuted(*meshes.jittered(14, 11), np.random.default_rng(3))
+    want = {}
+    for k, tri in enumerate(c):
+        for v in tri:
+            want[int(v)] = frozenset(int(t) for t in tri)   # later cells overwrite
+    for rank in range(world):
+        hm = L.host_analyse(x, c, rank=rank, world=world)
+        n2u, cl = hm["n2u"], hm["cells"].reshape(-1, 3)
+        lc = hm["last_cell"]
+        assert lc.size == (x.shape[0] if world == 1 else lc.size) and lc.min() >= 0
+        for i, k in enumerate(lc):
+            assert frozenset(int(n2u[v]) for v in cl[k]) == want[int(n2u[i])]
+
+
 def test_hilbert_order_is_local():
     """Consecutive internal ids are spatial neighbours: the tile halo stays small."""
     x, c = meshes.jittered(96, 96)
