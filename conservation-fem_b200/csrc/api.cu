@@ -925,6 +925,12 @@ int cfem_time_kernel(cfem_ctx* c, int kernel, int flux, int reps, double* ms_per
       case CFEM_KERNEL_ASM_RV_RHS:
         launch_rv_rhs(c, flux, CFEM_BDF2, dt, c->u_n, c->u_old, c->u_oo, nullptr, true, c->wk[8], c->fluxn);
         bytes = meta + 8.0 * 3 * nn + 16.0 * nn; break;
+      case CFEM_KERNEL_COMM_ALLREDUCE: {
+        double* sl[3] = {c->partials + 5 * kMaxPartials, c->partials + 6 * kMaxPartials, c->partials + 7 * kMaxPartials};
+        const int op[3] = {0, 1, 2};
+        allreduce_partials(c, 3, sl, op, 1184);
+        bytes = 24.0 * c->world; break; }
+      case CFEM_KERNEL_COMM_HALO: halo_exchange(c, c->u_n, 1); bytes = 8.0 * (double)(c->dm.nn - c->dm.no); break;
       default: CFEM_THROW(-1, "time_kernel: unknown kernel id");
     }
   };

@@ -112,6 +112,7 @@ struct P2P {
   unsigned long long halo_seq = 0, red_seq = 0;
   int32_t* d_send_ptr = nullptr;
   int32_t* d_peer_rank = nullptr;
+  P2PDev* d_dev = nullptr;   // device copy of d (for kernels that take it by pointer)
   int* h_error = nullptr;
 };
 
@@ -132,6 +133,10 @@ k_p2p_push(const P2PDev a, const double* __restrict__ v, const int width, const 
   }
   __threadfence_system();
   __syncthreads();
+  if (gridDim.x == 1) {  // small halos: one CTA, no ticket
+    if (threadIdx.x < a.npeer) *(volatile unsigned long long*)(a.peer_base[threadIdx.x] + 8 * a.rank) = seq;
+    return;
+  }
   __shared__ bool last;
   if (threadIdx.x == 0) {
     const unsigned int done = atomicAdd(a.counter, 1u);
@@ -228,6 +233,62 @@ k_p2p_allreduce(const P2PDev a, const SlotTable t, const int nslots, const int n
   }
 }
 
+// Low-latency variant: every scalar travels as two 8-byte words {32 data bits | 32-bit sequence tag}.
+// An aligned 8-byte store is delivered atomically, so the tag doubles as the arrival flag: no
+// __threadfence_system, no inter-CTA ticket, no separate flag store.  One CTA; warp w reduces slot w's
+// partials (fixed lane-strided order + shuffle tree), lanes 0..world-1 store the two words into every
+// rank's mailbox (own rank included), poll their own mailbox for the words of rank `lane`, and lane 0
+// folds the `world` values in rank order -- bitwise identical on every rank.  (One CTA; thread (slot, q)
+// handles slot `slot` to / from rank q.)
+__global__ void __launch_bounds__(kBlock)
+k_p2p_allreduce_ll(const P2PDev a, const SlotTable t, const int nslots, const int npart, const unsigned long long seq) {
+  __shared__ double red[9];
+  __shared__ double local_sum[8];
+  __shared__ double recv[8][kMaxWorld];
+  const int parity = (int)(seq & 1);
+  const unsigned int tag = (unsigned int)seq;
+  for (int slot = 0; slot < nslots; ++slot) {  // fixed order: bitwise reproducible
+    const double* p = t.p[slot];
+    const int op = t.op[slot];
+    double s = op == 0 ? 0.0 : (op == 1 ? INFINITY : -INFINITY);
+    for (int i = threadIdx.x; i < npart; i += kBlock) {
+      const double x = p[i];
+      s = op == 0 ? s + x : (op == 1 ? fmin(s, x) : fmax(s, x));
+    }
+    s = op == 0 ? block_sum(s, red) : (op == 1 ? block_min(s, red) : block_max(s, red));
+    if (threadIdx.x == 0) local_sum[slot] = s;
+  }
+  __syncthreads();
+  const size_t ll_off = kFlagBytes + kRedBytes;
+  if ((int)threadIdx.x < nslots * a.world) {
+    const int slot = threadIdx.x / a.world, q = threadIdx.x - slot * a.world;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(local_sum[slot]);
+    volatile unsigned long long* dst = (volatile unsigned long long*)(a.rank_base[q] + ll_off) +
+                                       (((size_t)parity * kMaxWorld + a.rank) * 8 + slot) * 2;
+    dst[0] = (bits & 0xffffffff00000000ull) | tag;
+    dst[1] = (bits << 32) | tag;
+    const volatile unsigned long long* src = (const volatile unsigned long long*)(a.local + ll_off) +
+                                             (((size_t)parity * kMaxWorld + q) * 8 + slot) * 2;
+    const long long t0 = clock64();
+    unsigned long long hi = src[0], lo = src[1];
+    while ((unsigned int)hi != tag || (unsigned int)lo != tag) {
+      if (clock64() - t0 > 60000000000LL) { *a.error = 1; break; }
+      hi = src[0]; lo = src[1];
+    }
+    recv[slot][q] = __longlong_as_double((long long)((hi & 0xffffffff00000000ull) | (lo >> 32)));
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nslots) {
+    const int op = t.op[threadIdx.x];
+    double r = recv[threadIdx.x][0];
+    for (int q = 1; q < a.world; ++q) {
+      const double x = recv[threadIdx.x][q];
+      r = op == 0 ? r + x : (op == 1 ? fmin(r, x) : fmax(r, x));
+    }
+    t.p[threadIdx.x][0] = r;
+  }
+}
+
 static void p2p_setup(cfem_ctx* c) {
   const HostMesh& hm = c->hm;
   const int world = c->world, rank = c->rank, npeer = (int)hm.peer_rank.size();
@@ -246,7 +307,7 @@ static void p2p_setup(cfem_ctx* c) {
   int64_t ng_max = 0;
   CUDA_OK(cudaMemcpy(&ng_max, dng, sizeof(int64_t), cudaMemcpyDeviceToHost));
   cudaFree(dng);
-  d.halo_off = kFlagBytes + kRedBytes;
+  d.halo_off = kFlagBytes + kRedBytes + kLLBytes;
   d.halo_stride = (((size_t)ng_max * 4 * sizeof(double)) + 255) / 256 * 256 + 256;
   const size_t bytes = d.halo_off + 2 * d.halo_stride;
   void* box = nullptr;
@@ -307,6 +368,9 @@ static void p2p_setup(cfem_ctx* c) {
   CUDA_OK(cudaMallocHost((void**)&pp->h_error, sizeof(int)));
   *pp->h_error = 0;
   d.error = pp->h_error;
+  CUDA_OK(cudaMalloc((void**)&pp->d_dev, sizeof(P2PDev)));
+  CUDA_OK(cudaMemcpy(pp->d_dev, &d, sizeof(P2PDev), cudaMemcpyHostToDevice));
+  c->allocs.push_back(pp->d_dev);
   // every rank must have its mailbox mapped everywhere before the first exchange: one tiny all-reduce
   double* tmp = c->partials;
   NCCL_OK(nccl().AllReduce(tmp, tmp, 1, ncclDouble, ncclSum, comm, c->stream));
@@ -376,7 +440,7 @@ void halo_exchange(cfem_ctx* c, double* v, int width) {
 // Producer half of a halo exchange for a vector that a SpMV-type kernel is about to read: pushes
 // the owned boundary values to the neighbours and returns where the consumer finds its ghosts.
 // (NCCL mode: does the whole exchange and returns an empty GhostSrc.)
-GhostSrc halo_push(cfem_ctx* c, double* v, bool gated) {
+GhostSrc halo_push(cfem_ctx* c, double* v, bool gated, bool in_consumer) {
   GhostSrc g;
   if (c->world == 1) {
     // measurement hook: CFEM_FORCE_GHOST=1 runs the ghost-aware kernel variants on one GPU (no ghosts, no waiting)
@@ -392,11 +456,18 @@ GhostSrc halo_push(cfem_ctx* c, double* v, bool gated) {
   ProfScope ps(c, PROF_COMM);
   P2P* pp = (P2P*)c->p2p;
   const unsigned long long seq = ++pp->halo_seq;
-  int grid = (int)((hm.send_idx.size() + kBlock - 1) / kBlock);
-  if (grid < 1) grid = 1;
-  if (grid > 32) grid = 32;
-  k_p2p_push<<<grid, kBlock, 0, c->stream>>>(pp->d, v, 1, seq, gated ? c->status : nullptr);
-  LAUNCHED(c);
+  // CFEM_PUSH=kernel: always a separate push kernel; CFEM_PUSH=multi: that kernel with the multi-CTA ticket
+  static const std::string push_mode = getenv("CFEM_PUSH") ? getenv("CFEM_PUSH") : "";
+  const bool fuse = in_consumer && push_mode.empty() && hm.send_idx.size() <= 16384;
+  if (!fuse) {
+    int grid = (int)((hm.send_idx.size() + kBlock - 1) / kBlock);
+    if (grid > 32) grid = 32;
+    if (grid < 1 || (hm.send_idx.size() <= 8192 && push_mode != "multi")) grid = 1;
+    k_p2p_push<<<grid, kBlock, 0, c->stream>>>(pp->d, v, 1, seq, gated ? c->status : nullptr);
+    LAUNCHED(c);
+  } else {
+    g.pushdev = pp->d_dev;
+  }
   c->halo_exchanges++;
   g.mbox = (const double*)(pp->d.local + pp->d.halo_off + (seq & 1) * pp->d.halo_stride);
   g.flags = pp->d.local;
@@ -432,7 +503,9 @@ int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int*
   for (int k = 0; k < nslots; ++k) { t.p[k] = slots[k]; t.op[k] = ops[k]; }
   if (c->p2p) {
     P2P* pp = (P2P*)c->p2p;
-    k_p2p_allreduce<<<nslots, kBlock, 0, c->stream>>>(pp->d, t, nslots, npart, ++pp->red_seq);
+    static const bool ticket = getenv("CFEM_ALLREDUCE") && std::string(getenv("CFEM_ALLREDUCE")) == "ticket";
+    if (ticket) k_p2p_allreduce<<<nslots, kBlock, 0, c->stream>>>(pp->d, t, nslots, npart, ++pp->red_seq);
+    else k_p2p_allreduce_ll<<<1, kBlock, 0, c->stream>>>(pp->d, t, nslots, npart, ++pp->red_seq);
     LAUNCHED(c);
     c->allreduces++;
     return 1;

@@ -64,7 +64,8 @@ void comm_setup_exchange(cfem_ctx* c);   // after the device arrays exist: maps 
 void comm_check(cfem_ctx* c);            // throws if a peer-memory exchange timed out
 void halo_exchange(cfem_ctx* c, double* v, int width = 1);   // width doubles per node (1, 2 or 4)
 struct GhostSrc;
-GhostSrc halo_push(cfem_ctx* c, double* v, bool gated);     // producer half only (see p2p.cuh)
+// producer half only (see p2p.cuh); in_consumer: do not launch anything, the consumer's CTA 0 pushes
+GhostSrc halo_push(cfem_ctx* c, double* v, bool gated, bool in_consumer = false);
 // local reduce of each partial array to its element 0 + all-reduce; returns the partial count to use after
 int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int* ops /*0 sum,1 min,2 max*/, int npart);
 int allreduce_sum1(cfem_ctx* c, double* slot, int npart);

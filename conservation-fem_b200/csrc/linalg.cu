@@ -152,6 +152,11 @@ k_spmv_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
               const int32_t* __restrict__ colidx, const double* __restrict__ vals, const double* __restrict__ x,
               double* __restrict__ y, const double* __restrict__ d0, const double* __restrict__ d1,
               double* __restrict__ part0, double* __restrict__ part1, const int32_t* __restrict__ status) {
+  int bid = blockIdx.x, nblk = gridDim.x;
+  if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
+    if (bid == 0) { push_cta(gsrc.pushdev, x, gsrc.seq, status && status[0]); return; }
+    --bid; --nblk;
+  }
   if (status && status[0]) return;
   __shared__ double prod[kTileNnzCap];
   __shared__ int32_t rp[kTileNodes + 1];
@@ -160,7 +165,7 @@ k_spmv_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
   double acc0 = 0.0, acc1 = 0.0;
   bool waited = false;
   const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;  // mbox_shifted[col] == mailbox[col - no]
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  for (int t = bid; t < ntiles; t += nblk) {
     const int tile = GHOST ? tile_order[t] : t;
     if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
     const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
@@ -194,11 +199,11 @@ k_spmv_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
   }
   if (NDOT >= 1) {
     acc0 = block_sum(acc0, red);
-    if (tid == 0) part0[blockIdx.x] = acc0;
+    if (tid == 0) part0[bid] = acc0;
   }
   if (NDOT >= 2) {
     acc1 = block_sum(acc1, red);
-    if (tid == 0) part1[blockIdx.x] = acc1;
+    if (tid == 0) part1[bid] = acc1;
   }
 }
 
@@ -413,13 +418,13 @@ template <int NDOT>
 static void spmv_dots(cfem_ctx* c, const Matrix& A, const double* x, double* y, const double* d0,
                       const double* d1, double* p0, double* p1, bool gated) {
   GhostSrc gsrc;
-  if (spmv_mode() == 0) gsrc = halo_push(c, const_cast<double*>(x), gated);  // producer half; the kernel waits in its boundary CTAs
+  if (spmv_mode() == 0) gsrc = halo_push(c, const_cast<double*>(x), gated, !g_spmv_tma);  // producer half; the kernel waits in its boundary CTAs
   else halo_exchange(c, const_cast<double*>(x));
   ProfScope ps(c, PROF_SPMV);
   if (spmv_mode() == 0 && g_spmv_tma)
     launch_tile_spmv(c, gsrc, A, x, EpSpmv<NDOT>{y, d0, d1, p0, p1}, gated);
   else if (spmv_mode() == 0 && gsrc.mbox)
-    k_spmv_stream<NDOT, true><<<spmv_grid(c), kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior,
+    k_spmv_stream<NDOT, true><<<spmv_grid(c) + (gsrc.pushdev ? 1 : 0), kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior,
                                                                           c->dm.ntiles, c->dm.tile_node, c->dm.rowptr,
                                                                           c->dm.colidx, A.vals, x, y, d0, d1, p0, p1,
                                                                           gated ? c->status : nullptr);
@@ -458,6 +463,11 @@ k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
               const double* __restrict__ b, const double* __restrict__ xk, double* __restrict__ xn,
               double* __restrict__ d, const double c1, const double c2, double* __restrict__ part_rr,
               double* __restrict__ part_bb) {
+  int bid = blockIdx.x, nblk = gridDim.x;
+  if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
+    if (bid == 0) { push_cta(gsrc.pushdev, xk, gsrc.seq, false); return; }
+    --bid; --nblk;
+  }
   __shared__ double prod[kTileNnzCap];
   __shared__ int32_t rp[kTileNodes + 1];
   __shared__ double red[9];
@@ -465,7 +475,7 @@ k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
   double rr = 0.0, bb = 0.0;
   bool waited = false;
   const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;  // mbox_shifted[col] == mailbox[col - no]
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  for (int t = bid; t < ntiles; t += nblk) {
     const int tile = GHOST ? tile_order[t] : t;
     if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
     const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
@@ -504,10 +514,10 @@ k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
     __syncthreads();
   }
   rr = block_sum(rr, red);
-  if (tid == 0) part_rr[blockIdx.x] = rr;
+  if (tid == 0) part_rr[bid] = rr;
   if (FIRST) {
     bb = block_sum(bb, red);
-    if (tid == 0) part_bb[blockIdx.x] = bb;
+    if (tid == 0) part_bb[bid] = bb;
   }
 }
 
@@ -537,10 +547,10 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
   if (target > max_it) target = max_it;
   while (true) {
     for (; it < target; ++it) {
-      const GhostSrc gsrc = halo_push(c, xa, false);
+      const GhostSrc gsrc = halo_push(c, xa, false, !g_spmv_tma);
       ProfScope ps(c, PROF_CHEB);
 #define CHEB_LAUNCH(FIRST, GHOST, C1, C2, PBB)                                                                   \
-  k_cheb_stream<FIRST, GHOST><<<gs, kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior, \
+  k_cheb_stream<FIRST, GHOST><<<gs + (GHOST && gsrc.pushdev ? 1 : 0), kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior, \
       c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, A.dinv, b, xa, xb, d, C1, C2,              \
       part + P_RR * kMaxPartials, PBB)
       if (g_spmv_tma && it == 0) {

@@ -242,7 +242,8 @@ int cfem_step_euler(cfem_ctx* ctx, const cfem_step_params* p, int n_steps, cfem_
  * back-to-back launches of one hot kernel on the resident state, and the
  * algorithmic bytes one launch moves. */
 enum { CFEM_KERNEL_SPMV = 0, CFEM_KERNEL_ASM_RESIDUAL = 1, CFEM_KERNEL_ASM_JACOBIAN = 2,
-       CFEM_KERNEL_RV_EPSILON = 3, CFEM_KERNEL_ASM_RV_RHS = 4, CFEM_KERNEL_PCG_ITER = 5 };
+       CFEM_KERNEL_RV_EPSILON = 3, CFEM_KERNEL_ASM_RV_RHS = 4, CFEM_KERNEL_PCG_ITER = 5,
+       CFEM_KERNEL_COMM_ALLREDUCE = 6 /* 3-scalar all-reduce over the ranks */, CFEM_KERNEL_COMM_HALO = 7 /* full halo exchange of one field */ };
 /* Bracket every kernel launch of the following calls with CUDA events (adds ~2 us
  * per launch; use on a separate pass, not on the timed one).  cfem_profile_end sums
  * the device time and launch count per category:
