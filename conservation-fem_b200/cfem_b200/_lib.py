@@ -101,6 +101,8 @@ SIGNATURES = {
     "cfem_state_set": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _D]),
     "cfem_state_update": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _D]),
     "cfem_state_get": (_I, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(_D)]),
+    "cfem_state_update_owned": (_I, [_P, _P, _P, _P, _P, _P, _D]),
+    "cfem_state_get_owned": (_I, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(_D)]),
     "cfem_step_scalar": (_I, [_P, C.POINTER(StepParams), _I, _P, C.POINTER(StepStats)]),
     "cfem_step_advection": (_I, [_P, C.POINTER(StepParams), _I, _I, C.POINTER(StepStats)]),
     "cfem_euler_state_set": (_I, [_P, _P, _P, _P, _P, _P, _P, _D]),

@@ -236,6 +236,24 @@ class Context:
         bufs["t"] = t.value
         return bufs
 
+    def state_update_owned(self, uh=None, u_n=None, u_old=None, u_oo=None, RH=None, t=0.0):
+        """``state_set(keep_predictions=True)`` with the fields in this rank's owned order (entry i is caller dof
+        ``owned_dofs()[i]``): one contiguous copy per field, no global-sized arrays."""
+        args = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (uh, u_n, u_old, u_oo, RH)]
+        for a in args:
+            if a is not None and a.size != self.n_owned:
+                raise ValueError("owned-layout fields must have n_owned entries")
+        self._keep = args
+        L.check(self._lib.cfem_state_update_owned(self._h, *[L.ptr(a) for a in args], float(t)))
+
+    def state_get_owned(self, names=("uh",), out=None):
+        order = ("uh", "u_n", "u_old", "u_oo", "RH", "eps")
+        bufs = {k: ((out or {}).get(k) if out and k in out else np.empty(self.n_owned)) for k in names if k in order}
+        t = C.c_double(0.0)
+        L.check(self._lib.cfem_state_get_owned(self._h, *[L.ptr(bufs.get(k)) for k in order], C.byref(t)))
+        bufs["t"] = t.value
+        return bufs
+
     def step_scalar(self, params: "L.StepParams", n_steps=1, bc_values=None):
         st = L.StepStats()
         bc_values = _field(bc_values)

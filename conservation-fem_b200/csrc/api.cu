@@ -615,6 +615,33 @@ int cfem_state_get(cfem_ctx* c, double* uh, double* u_n, double* u_old, double* 
   API_END
 }
 
+int cfem_state_update_owned(cfem_ctx* c, const double* uh, const double* u_n, const double* u_old,
+                            const double* u_oo, const double* RH, double t) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  const double* src[5] = {uh, u_n, u_old, u_oo, RH};
+  double* dst[5] = {c->uh, c->u_n, c->u_old, c->u_oo, c->RH};
+  for (int k = 0; k < 5; ++k)
+    if (src[k]) CUDA_OK(cudaMemcpyAsync(dst[k], src[k], c->dm.no * sizeof(double), cudaMemcpyDefault, c->stream));
+  for (int k = 0; k < 5; ++k)
+    if (src[k]) halo_exchange(c, dst[k]);
+  c->t = t;
+  API_END
+}
+
+int cfem_state_get_owned(cfem_ctx* c, double* uh, double* u_n, double* u_old, double* u_oo, double* RH, double* eps,
+                         double* t) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  double* dst[6] = {uh, u_n, u_old, u_oo, RH, eps};
+  const double* src[6] = {c->uh, c->u_n, c->u_old, c->u_oo, c->RH, c->eps};
+  for (int k = 0; k < 6; ++k)
+    if (dst[k]) CUDA_OK(cudaMemcpyAsync(dst[k], src[k], c->dm.no * sizeof(double), cudaMemcpyDefault, c->stream));
+  if (t) *t = c->t;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
 // sqrt(sum of the per-CTA partials) on the host (one sync)
 static double partials_norm(cfem_ctx* c, double* part, int npart) {
   npart = allreduce_sum1(c, part, npart);

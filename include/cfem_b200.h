@@ -213,6 +213,14 @@ int cfem_state_update(cfem_ctx* ctx, const double* uh, const double* u_n, const 
                       const double* u_oo, const double* RH, const double* h, const double* w, double t);
 int cfem_state_get(cfem_ctx* ctx, double* uh, double* u_n, double* u_old, double* u_oo,
                    double* RH, double* eps, double* t);
+/* Distributed hot loops without global arrays: the same two calls with the fields in THIS RANK'S owned
+ * order -- entry i belongs to caller dof ordering[i], i < cfem_num_owned (cfem_get_ordering), the layout a
+ * rank of an MPI run keeps its fields in.  One contiguous copy per field (host or device pointers), ghosts
+ * refreshed by a halo exchange; no permutation, no global-sized buffer.  Keeps the iteration predictions. */
+int cfem_state_update_owned(cfem_ctx* ctx, const double* uh, const double* u_n, const double* u_old,
+                            const double* u_oo, const double* RH, double t);
+int cfem_state_get_owned(cfem_ctx* ctx, double* uh, double* u_n, double* u_old, double* u_oo,
+                         double* RH, double* eps, double* t);
 
 /* n_steps passes of the loop body of KPP_exact.py:119-161 /
  * Exact_Burger_RV.py:170-224 on the resident state.  bc_values (CFEM_BC_USER):

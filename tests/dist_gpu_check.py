@@ -16,7 +16,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from cfem_b200 import Context, meshes, distributed as D, solvers as GS  # noqa: E402
+from cfem_b200 import Context, meshes, step_params, distributed as D, solvers as GS  # noqa: E402
 from oracle import solvers as S  # noqa: E402
 
 
@@ -49,6 +49,20 @@ def main():
     cs = ctx.comm_stats()
     if rank == 0:
         print(f"[dist x{world}] comm: {cs}", flush=True)
+    # owned-layout state calls: what comes back is the owned slice of the global field, and a state sent
+    # that way (ghosts refreshed by the halo exchange inside) steps exactly like the global-array one
+    own = ctx.owned_dofs()
+    g = ctx.state_get(("uh", "u_n", "u_old", "u_oo", "RH"))
+    o = ctx.state_get_owned(("uh", "u_n", "u_old", "u_oo", "RH"))
+    for k in ("uh", "u_n", "u_old", "u_oo", "RH"):
+        assert np.array_equal(o[k], g[k][own]), k
+    p = step_params("burgers", dt, 0.5, 10.0, scheme="bdf2", bc_kind="burgers_exact")
+    ctx.step_scalar(p, 1)
+    a = ctx.state_get_owned(("uh",))["uh"]
+    ctx.state_update_owned(uh=o["uh"], u_n=o["u_n"], u_old=o["u_old"], u_oo=o["u_oo"], RH=o["RH"], t=o["t"])
+    ctx.step_scalar(p, 1)
+    b = ctx.state_get_owned(("uh",))["uh"]
+    assert np.linalg.norm(a - b) <= 1e-12 * np.linalg.norm(a), np.abs(a - b).max()   # iteration predictions differ
     ctx.close()
 
     # KPP, unstructured + permuted numbering

@@ -197,6 +197,23 @@ def test_krylov_vs_lu(case, solver):
     assert ctx.last_relres <= 1e-13
 
 
+def test_owned_layout_state_roundtrip(case):
+    """cfem_state_update_owned / cfem_state_get_owned: entry i is caller dof ordering[i] (all dofs on one GPU)."""
+    _, x, c, ctx, m = case
+    uh, u_n, u_old, u_oo, rng = fields(m)
+    own = ctx.owned_dofs()
+    assert own.size == ctx.n_owned == m.n
+    ctx.state_set(uh=0 * uh, u_n=0 * uh, u_old=0 * uh, u_oo=0 * uh, RH=0 * uh, t=0.0)
+    ctx.state_update_owned(uh=uh[own], u_n=u_n[own], u_old=u_old[own], u_oo=u_oo[own], t=0.25)
+    g = ctx.state_get(("uh", "u_n", "u_old", "u_oo", "RH"))
+    assert np.array_equal(g["uh"], uh) and np.array_equal(g["u_n"], u_n) and np.array_equal(g["u_old"], u_old)
+    assert np.array_equal(g["u_oo"], u_oo) and not g["RH"].any() and g["t"] == 0.25
+    o = ctx.state_get_owned(("uh", "u_oo"))
+    assert np.array_equal(o["uh"], uh[own]) and np.array_equal(o["u_oo"], u_oo[own])
+    with pytest.raises(ValueError):
+        ctx.state_update_owned(uh=uh[:-1])
+
+
 def test_si_epsilon(case):
     """(f-1) smoothness-indicator viscosity, SI.py:38-67 / 147-192."""
     _, x, c, ctx, m = case
