@@ -6,6 +6,34 @@ namespace cfem {
 
 constexpr int kBlock = 256;  // threads per CTA for every kernel in the library
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with launch_pdl() may become resident while
+// the previous kernel of the stream is still draining.  pdl_wait() blocks until that kernel has completed and
+// its writes are visible (a no-op for ordinary launches) -- nothing that depends on the stream order may be
+// touched before it; pdl_launch() lets the NEXT kernel's CTAs take the slots this grid frees as it drains.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Host side: same as kern<<<grid, block, smem, stream>>>(args...) with programmatic stream serialisation allowed.
+// Only for kernels whose first statement is pdl_wait().  CFEM_PDL=0 falls back to plain launches.
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("CFEM_PDL") && std::string(getenv("CFEM_PDL")) == "0");
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

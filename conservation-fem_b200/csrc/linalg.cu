@@ -152,6 +152,8 @@ k_spmv_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
               const int32_t* __restrict__ colidx, const double* __restrict__ vals, const double* __restrict__ x,
               double* __restrict__ y, const double* __restrict__ d0, const double* __restrict__ d1,
               double* __restrict__ part0, double* __restrict__ part1, const int32_t* __restrict__ status) {
+  pdl_wait();
+  pdl_launch();
   int bid = blockIdx.x, nblk = gridDim.x;
   if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
     if (bid == 0) { push_cta(gsrc.pushdev, x, gsrc.seq, status && status[0]); return; }
@@ -424,15 +426,13 @@ static void spmv_dots(cfem_ctx* c, const Matrix& A, const double* x, double* y, 
   if (spmv_mode() == 0 && g_spmv_tma)
     launch_tile_spmv(c, gsrc, A, x, EpSpmv<NDOT>{y, d0, d1, p0, p1}, gated);
   else if (spmv_mode() == 0 && gsrc.mbox)
-    k_spmv_stream<NDOT, true><<<spmv_grid(c) + (gsrc.pushdev ? 1 : 0), kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior,
-                                                                          c->dm.ntiles, c->dm.tile_node, c->dm.rowptr,
-                                                                          c->dm.colidx, A.vals, x, y, d0, d1, p0, p1,
-                                                                          gated ? c->status : nullptr);
+    launch_pdl(k_spmv_stream<NDOT, true>, spmv_grid(c) + (gsrc.pushdev ? 1 : 0), kTileNodes, 0, c->stream, gsrc, c->dm.no,
+               c->dm.tile_order, c->dm.n_interior, c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, x, y,
+               d0, d1, p0, p1, gated ? c->status : nullptr);
   else if (spmv_mode() == 0)
-    k_spmv_stream<NDOT, false><<<spmv_grid(c), kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior,
-                                                                           c->dm.ntiles, c->dm.tile_node, c->dm.rowptr,
-                                                                           c->dm.colidx, A.vals, x, y, d0, d1, p0, p1,
-                                                                           gated ? c->status : nullptr);
+    launch_pdl(k_spmv_stream<NDOT, false>, spmv_grid(c), kTileNodes, 0, c->stream, gsrc, c->dm.no, c->dm.tile_order,
+               c->dm.n_interior, c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, x, y, d0, d1, p0, p1,
+               gated ? c->status : nullptr);
   else
     k_spmv<8, NDOT><<<spmv_grid(c), kBlock, 0, c->stream>>>(c->dm.no, c->dm.rowptr, c->dm.colidx, A.vals, x, y, d0,
                                                             d1, p0, p1, gated ? c->status : nullptr);
@@ -463,6 +463,8 @@ k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
               const double* __restrict__ b, const double* __restrict__ xk, double* __restrict__ xn,
               double* __restrict__ d, const double c1, const double c2, double* __restrict__ part_rr,
               double* __restrict__ part_bb) {
+  pdl_wait();
+  pdl_launch();
   int bid = blockIdx.x, nblk = gridDim.x;
   if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
     if (bid == 0) { push_cta(gsrc.pushdev, xk, gsrc.seq, false); return; }
@@ -550,9 +552,9 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
       const GhostSrc gsrc = halo_push(c, xa, false, !g_spmv_tma);
       ProfScope ps(c, PROF_CHEB);
 #define CHEB_LAUNCH(FIRST, GHOST, C1, C2, PBB)                                                                   \
-  k_cheb_stream<FIRST, GHOST><<<gs + (GHOST && gsrc.pushdev ? 1 : 0), kTileNodes, 0, c->stream>>>(gsrc, c->dm.no, c->dm.tile_order, c->dm.n_interior, \
-      c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, A.dinv, b, xa, xb, d, C1, C2,              \
-      part + P_RR * kMaxPartials, PBB)
+  launch_pdl(k_cheb_stream<FIRST, GHOST>, gs + (GHOST && gsrc.pushdev ? 1 : 0), kTileNodes, 0, c->stream, gsrc, c->dm.no, \
+             c->dm.tile_order, c->dm.n_interior, c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, A.dinv, \
+             b, xa, xb, d, C1, C2, part + P_RR * kMaxPartials, PBB)
       if (g_spmv_tma && it == 0) {
         launch_tile_spmv(c, gsrc, A, xa, EpCheb<true>{A.dinv, b, xa, xb, d, 0.0, 1.0 / theta, part + P_RR * kMaxPartials, part + P_BB * kMaxPartials}, false);
       } else if (g_spmv_tma) {
@@ -739,6 +741,8 @@ __global__ void __launch_bounds__(kBlock)
 k_bi_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q, const double* __restrict__ dinv,
           double* __restrict__ r, double* __restrict__ rhat, double* __restrict__ p, double* __restrict__ y,
           double* __restrict__ part, int32_t* __restrict__ status) {
+  pdl_wait();
+  pdl_launch();
   __shared__ double red[9];
   double rr = 0.0, bb = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
@@ -760,6 +764,8 @@ __global__ void __launch_bounds__(kBlock)
 k_bi_p(int64_t n, const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
        double* __restrict__ p, double* __restrict__ y, const double* __restrict__ part, int npart, int cur,
        double* __restrict__ scalars, int32_t* __restrict__ status, double rtol2, double atol2) {
+  pdl_wait();
+  pdl_launch();
   if (status[0]) return;
   __shared__ double red[9];
   const double rho_old = reduce_partials(part + (cur ? P_RZ0 : P_RZ1) * kMaxPartials, npart, red);
@@ -787,6 +793,8 @@ __global__ void __launch_bounds__(kBlock)
 k_bi_s(int64_t n, const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
        double* __restrict__ s, double* __restrict__ z, const double* __restrict__ part, int npart_vec,
        int npart_spmv, int cur, double* __restrict__ scalars, const int32_t* __restrict__ status) {
+  pdl_wait();
+  pdl_launch();
   if (status[0]) return;
   __shared__ double red[9];
   const double rho = reduce_partials(part + (cur ? P_RZ1 : P_RZ0) * kMaxPartials, npart_vec, red);
@@ -805,6 +813,8 @@ k_bi_x(int64_t n, const double* __restrict__ y, const double* __restrict__ z, co
        const double* __restrict__ t, const double* __restrict__ rhat, double* __restrict__ x, double* __restrict__ r,
        double* __restrict__ part, int npart_spmv, int cur, double* __restrict__ scalars,
        const int32_t* __restrict__ status) {
+  pdl_wait();
+  pdl_launch();
   if (status[0]) return;
   __shared__ double red[9];
   const double ts = reduce_partials(part + P_A * kMaxPartials, npart_spmv, red);
@@ -838,7 +848,7 @@ SolveResult bicgstab_generic(cfem_ctx* c, int64_t n, int halo_width, const doubl
   const int npv = dist ? 1 : gv;  // partial counts seen by consumers of vector-kernel partials
   const int sum3[3] = {0, 0, 0};
   apply(x, v, 0, nullptr, nullptr, nullptr, nullptr, false);
-  { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_init<<<gv, kBlock, 0, c->stream>>>(n, b, v, dinv, r, rhat, p, y, part, c->status); LAUNCHED(c); }
+  { ProfScope ps(c, PROF_KRYLOV_VEC); launch_pdl(k_bi_init, gv, kBlock, 0, c->stream, n, b, v, dinv, r, rhat, p, y, part, c->status); LAUNCHED(c); }
   { double* sl[3] = {part + P_RR * kMaxPartials, part + P_RZ0 * kMaxPartials, part + P_BB * kMaxPartials}; allreduce_partials(c, 3, sl, sum3, gv); }
   { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, npv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
   SolveResult res{0, 0.0, false};
@@ -847,13 +857,13 @@ SolveResult bicgstab_generic(cfem_ctx* c, int64_t n, int halo_width, const doubl
     const int cur = it & 1;  // rho of this iteration lives in RZ[cur]
     if (it > 0) {
       ProfScope ps(c, PROF_KRYLOV_VEC);
-      k_bi_p<<<gv, kBlock, 0, c->stream>>>(n, r, v, dinv, p, y, part, npv, cur, c->scalars, c->status, rtol2, atol2);
+      launch_pdl(k_bi_p, gv, kBlock, 0, c->stream, n, r, v, dinv, p, y, part, npv, cur, c->scalars, c->status, rtol2, atol2);
       LAUNCHED(c);
     }
     const int nps1 = apply(y, v, 1, rhat, nullptr, part + P_PQ * kMaxPartials, nullptr, true);
-    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_s<<<gv, kBlock, 0, c->stream>>>(n, r, v, dinv, s, z, part, npv, nps1, cur, c->scalars, c->status); LAUNCHED(c); }
+    { ProfScope ps(c, PROF_KRYLOV_VEC); launch_pdl(k_bi_s, gv, kBlock, 0, c->stream, n, r, v, dinv, s, z, part, npv, nps1, cur, c->scalars, c->status); LAUNCHED(c); }
     const int nps2 = apply(z, t, 2, s, t, part + P_A * kMaxPartials, part + P_B * kMaxPartials, true);
-    { ProfScope ps(c, PROF_KRYLOV_VEC); k_bi_x<<<gv, kBlock, 0, c->stream>>>(n, y, z, s, t, rhat, x, r, part, nps2, cur, c->scalars, c->status); LAUNCHED(c); }
+    { ProfScope ps(c, PROF_KRYLOV_VEC); launch_pdl(k_bi_x, gv, kBlock, 0, c->stream, n, y, z, s, t, rhat, x, r, part, nps2, cur, c->scalars, c->status); LAUNCHED(c); }
     { double* sl[2] = {part + (cur ? P_RZ0 : P_RZ1) * kMaxPartials, part + P_RR * kMaxPartials}; allreduce_partials(c, 2, sl, sum3, gv); }
     ++it;
     if (it >= next_poll || it == max_it) {
