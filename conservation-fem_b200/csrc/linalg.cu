@@ -152,27 +152,33 @@ k_spmv_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
               const int32_t* __restrict__ colidx, const double* __restrict__ vals, const double* __restrict__ x,
               double* __restrict__ y, const double* __restrict__ d0, const double* __restrict__ d1,
               double* __restrict__ part0, double* __restrict__ part1, const int32_t* __restrict__ status) {
-  pdl_wait();
-  pdl_launch();
+  // Everything up to pdl_wait() reads mesh tables only, so under a programmatic launch it overlaps the
+  // previous kernel's drain; x, status, the mailbox and the partials are touched after it.
   int bid = blockIdx.x, nblk = gridDim.x;
   if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
-    if (bid == 0) { push_cta(gsrc.pushdev, x, gsrc.seq, status && status[0]); return; }
+    if (bid == 0) { pdl_wait(); pdl_launch(); push_cta(gsrc.pushdev, x, gsrc.seq, status && status[0]); return; }
     --bid; --nblk;
   }
-  if (status && status[0]) return;
   __shared__ double prod[kTileNnzCap];
   __shared__ int32_t rp[kTileNodes + 1];
   __shared__ double red[9];
   const int tid = threadIdx.x;
   double acc0 = 0.0, acc1 = 0.0;
-  bool waited = false;
+  bool waited = false, synced = false;
   const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;  // mbox_shifted[col] == mailbox[col - no]
+  if (bid >= ntiles) { pdl_wait(); pdl_launch(); }
   for (int t = bid; t < ntiles; t += nblk) {
     const int tile = GHOST ? tile_order[t] : t;
-    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
     const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
     for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i];
     __syncthreads();
+    if (!synced) {
+      pdl_wait();
+      pdl_launch();
+      synced = true;
+      if (status && status[0]) return;
+    }
+    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
     const int start = rp[0], cnt = rp[nrows] - start;
     const double* __restrict__ v = vals + start;
     const int32_t* __restrict__ ci = colidx + start;
@@ -463,11 +469,9 @@ k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
               const double* __restrict__ b, const double* __restrict__ xk, double* __restrict__ xn,
               double* __restrict__ d, const double c1, const double c2, double* __restrict__ part_rr,
               double* __restrict__ part_bb) {
-  pdl_wait();
-  pdl_launch();
   int bid = blockIdx.x, nblk = gridDim.x;
   if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
-    if (bid == 0) { push_cta(gsrc.pushdev, xk, gsrc.seq, false); return; }
+    if (bid == 0) { pdl_wait(); pdl_launch(); push_cta(gsrc.pushdev, xk, gsrc.seq, false); return; }
     --bid; --nblk;
   }
   __shared__ double prod[kTileNnzCap];
@@ -475,14 +479,16 @@ k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
   __shared__ double red[9];
   const int tid = threadIdx.x;
   double rr = 0.0, bb = 0.0;
-  bool waited = false;
+  bool waited = false, synced = false;
   const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;  // mbox_shifted[col] == mailbox[col - no]
+  if (bid >= ntiles) { pdl_wait(); pdl_launch(); }
   for (int t = bid; t < ntiles; t += nblk) {
     const int tile = GHOST ? tile_order[t] : t;
-    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
     const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
     for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i];
     __syncthreads();
+    if (!synced) { pdl_wait(); pdl_launch(); synced = true; }   // mesh tables only above (see k_spmv_stream)
+    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
     const int start = rp[0], cnt = rp[nrows] - start;
     const double* __restrict__ v = vals + start;
     const int32_t* __restrict__ ci = colidx + start;
