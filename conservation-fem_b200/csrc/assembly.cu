@@ -372,6 +372,8 @@ template <class Op>
 __global__ void __launch_bounds__(kTileNodes)
 k_tile_assemble(const DevMesh m, const Op op, const bool bc, double* __restrict__ vals,
                 double* __restrict__ dinv, double* __restrict__ partials, const int ccap, const int nnzcap) {
+  pdl_wait();
+  pdl_launch();
   constexpr int NV = Op::NV;
   constexpr bool MAT = Op::MAT;
   extern __shared__ double smem[];
@@ -480,7 +482,7 @@ static int run_tiles(cfem_ctx* c, const Op& op, bool bc, double* vals, double* d
   if (grid > c->dm.ntiles) grid = c->dm.ntiles;
   if (grid > kMaxPartials) grid = kMaxPartials;
   ProfScope ps(c, Op::MAT ? PROF_ASM_MAT : PROF_ASM_VEC);
-  k_tile_assemble<Op><<<grid, kTileNodes, smem, c->stream>>>(c->dm, op, bc, vals, dinv, partials, ccap, nnzcap);
+  launch_pdl(k_tile_assemble<Op>, grid, kTileNodes, smem, c->stream, c->dm, op, bc, vals, dinv, partials, ccap, nnzcap);
   CUDA_OK(cudaGetLastError());
   c->launches.total++;
   c->launches.assembly++;

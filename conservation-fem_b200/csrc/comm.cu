@@ -242,6 +242,8 @@ k_p2p_allreduce(const P2PDev a, const SlotTable t, const int nslots, const int n
 // handles slot `slot` to / from rank q.)
 __global__ void __launch_bounds__(kBlock)
 k_p2p_allreduce_ll(const P2PDev a, const SlotTable t, const int nslots, const int npart, const unsigned long long seq) {
+  pdl_wait();
+  pdl_launch();
   __shared__ double red[9];
   __shared__ double local_sum[8];
   __shared__ double recv[8][kMaxWorld];
@@ -505,7 +507,7 @@ int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int*
     P2P* pp = (P2P*)c->p2p;
     static const bool ticket = getenv("CFEM_ALLREDUCE") && std::string(getenv("CFEM_ALLREDUCE")) == "ticket";
     if (ticket) k_p2p_allreduce<<<nslots, kBlock, 0, c->stream>>>(pp->d, t, nslots, npart, ++pp->red_seq);
-    else k_p2p_allreduce_ll<<<1, kBlock, 0, c->stream>>>(pp->d, t, nslots, npart, ++pp->red_seq);
+    else launch_pdl(k_p2p_allreduce_ll, 1, kBlock, 0, c->stream, pp->d, t, nslots, npart, ++pp->red_seq);
     LAUNCHED(c);
     c->allreduces++;
     return 1;

@@ -42,6 +42,8 @@ __global__ void k_fill(double* __restrict__ dst, double v, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) dst[i] = v;
 }
 __global__ void k_sub(double* __restrict__ x, const double* __restrict__ dx, int64_t n) {
+  pdl_wait();
+  pdl_launch();
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) x[i] -= dx[i];
 }
 __global__ void k_norm2(const double* __restrict__ v, int64_t n, double* __restrict__ partials) {
@@ -81,7 +83,7 @@ void launch_copy(cfem_ctx* c, double* dst, const double* src, int64_t n) {
 }
 void launch_sub(cfem_ctx* c, double* x, const double* dx, int64_t n) {
   ProfScope ps(c, PROF_MISC);
-  k_sub<<<vec_grid(c, n), kBlock, 0, c->stream>>>(x, dx, n); LAUNCHED(c);
+  launch_pdl(k_sub, vec_grid(c, n), kBlock, 0, c->stream, x, dx, n); LAUNCHED(c);
 }
 
 double norm2(cfem_ctx* c, const double* v, int64_t n) {
@@ -532,6 +534,8 @@ k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
 // writes sqrt(rr/bb) to scalars[S_RELRES] from the partials
 __global__ void __launch_bounds__(kBlock)
 k_relres(const double* __restrict__ part, int npart_rr, int npart_bb, double* __restrict__ scalars) {
+  pdl_wait();
+  pdl_launch();
   __shared__ double red[9];
   const double rr = reduce_partials(part + P_RR * kMaxPartials, npart_rr, red);
   const double bb = reduce_partials(part + P_BB * kMaxPartials, npart_bb, red);
@@ -584,7 +588,7 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
     }
     // the last kernel measured ||b - M x_{it-1}||; x_it is one update further on
     const int np_rr = allreduce_sum1(c, part + P_RR * kMaxPartials, gs);
-    { ProfScope ps(c, PROF_KRYLOV_VEC); k_relres<<<1, kBlock, 0, c->stream>>>(part, np_rr, np_bb, c->scalars); LAUNCHED(c); }
+    { ProfScope ps(c, PROF_KRYLOV_VEC); launch_pdl(k_relres, 1, kBlock, 0, c->stream, part, np_rr, np_bb, c->scalars); LAUNCHED(c); }
     CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + S_RELRES, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     res.iters = it;
@@ -635,6 +639,8 @@ k_pcg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q
 __global__ void __launch_bounds__(kBlock)
 k_check(const double* __restrict__ part, int npart, double* __restrict__ scalars, int32_t* __restrict__ status,
         double rtol2, double atol2, int first, int iters_if_stop) {
+  pdl_wait();
+  pdl_launch();
   __shared__ double red[9];
   if (status[0]) return;
   const double rr = reduce_partials(part + P_RR * kMaxPartials, npart, red);
@@ -720,7 +726,7 @@ SolveResult pcg(cfem_ctx* c, const Matrix& A, const double* b, double* x, double
   launch_spmv(c, A, x, q);
   { ProfScope ps(c, PROF_KRYLOV_VEC); k_pcg_init<<<gv, kBlock, 0, c->stream>>>(n, b, q, A.dinv, r, z, p, part, c->status); LAUNCHED(c); }
   { double* sl[3] = {part + P_RZ0 * kMaxPartials, part + P_RR * kMaxPartials, part + P_BB * kMaxPartials}; allreduce_partials(c, 3, sl, sum2, gv); }
-  { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, npv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
+  { ProfScope ps(c, PROF_KRYLOV_VEC); launch_pdl(k_check, 1, kBlock, 0, c->stream, part, npv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
   SolveResult res{0, 0.0, false};
   int it = 0, next_poll = predict ? (*predict > 2 ? *predict - 1 : 1) : 4;
   while (it < max_it) {
@@ -856,7 +862,7 @@ SolveResult bicgstab_generic(cfem_ctx* c, int64_t n, int halo_width, const doubl
   apply(x, v, 0, nullptr, nullptr, nullptr, nullptr, false);
   { ProfScope ps(c, PROF_KRYLOV_VEC); launch_pdl(k_bi_init, gv, kBlock, 0, c->stream, n, b, v, dinv, r, rhat, p, y, part, c->status); LAUNCHED(c); }
   { double* sl[3] = {part + P_RR * kMaxPartials, part + P_RZ0 * kMaxPartials, part + P_BB * kMaxPartials}; allreduce_partials(c, 3, sl, sum3, gv); }
-  { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, npv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
+  { ProfScope ps(c, PROF_KRYLOV_VEC); launch_pdl(k_check, 1, kBlock, 0, c->stream, part, npv, c->scalars, c->status, rtol2, atol2, 1, 0); LAUNCHED(c); }
   SolveResult res{0, 0.0, false};
   int it = 0, next_poll = predict ? (*predict > 2 ? *predict - 1 : 1) : 4;
   while (it < max_it) {
@@ -874,7 +880,7 @@ SolveResult bicgstab_generic(cfem_ctx* c, int64_t n, int halo_width, const doubl
     ++it;
     if (it >= next_poll || it == max_it) {
       // the convergence test for iteration `it` runs inside the next k_bi_p; issue a stand-alone check
-      { ProfScope ps(c, PROF_KRYLOV_VEC); k_check<<<1, kBlock, 0, c->stream>>>(part, npv, c->scalars, c->status, rtol2, atol2, 0, it); LAUNCHED(c); }
+      { ProfScope ps(c, PROF_KRYLOV_VEC); launch_pdl(k_check, 1, kBlock, 0, c->stream, part, npv, c->scalars, c->status, rtol2, atol2, 0, it); LAUNCHED(c); }
       if (poll_done(c, res)) break;
       next_poll = it + 2;
     }

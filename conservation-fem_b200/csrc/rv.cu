@@ -33,6 +33,8 @@ template <int FLUX>
 __global__ void __launch_bounds__(kBlock)
 k_stats(int64_t n_owned, int64_t n_local, const double* __restrict__ v, double* __restrict__ beta,
         double* __restrict__ part) {
+  pdl_wait();
+  pdl_launch();
   __shared__ double red[9];
   double s = 0.0, mn = INFINITY, mx = -INFINITY;
   const int64_t n = FLUX >= 0 ? n_local : n_owned;  // beta is also needed on the ghosts
@@ -76,6 +78,8 @@ k_epsilon_stream(const int ntiles, const int64_t nn, const int32_t* __restrict__
                  const double* __restrict__ u_n, const double* __restrict__ Rh, const double* __restrict__ beta,
                  const double2* __restrict__ w, const double* __restrict__ h, const double* __restrict__ part,
                  int npart, double Cvel, double Crv, double* __restrict__ eps) {
+  pdl_wait();
+  pdl_launch();
   __shared__ double val[kTileNnzCap];
   __shared__ int32_t col[kTileNnzCap];
   __shared__ int32_t rp[kTileNodes + 1];
@@ -198,7 +202,7 @@ static int stats_allreduce(cfem_ctx* c, int gv) {
 
 void launch_stats(cfem_ctx* c, const double* v) {
   const int gv = vec_grid(c, c->dm.nn);
-  k_stats<-1><<<gv, kBlock, 0, c->stream>>>(c->dm.no, c->dm.nn, v, nullptr, c->partials); LAUNCHED(c);
+  launch_pdl(k_stats<-1>, gv, kBlock, 0, c->stream, c->dm.no, c->dm.nn, v, nullptr, c->partials); LAUNCHED(c);
   stats_allreduce(c, gv);
 }
 
@@ -210,7 +214,7 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
   int np = gv;
   if (variant == CFEM_EPS_CELL) {
     if (!u_n || !Rh || !w) CFEM_THROW(-1, "rv_epsilon(cell): u_n, Rh and w are required");
-    k_stats<-1><<<gv, kBlock, 0, c->stream>>>(n, nl, u_n, nullptr, c->partials); LAUNCHED(c);
+    launch_pdl(k_stats<-1>, gv, kBlock, 0, c->stream, n, nl, u_n, nullptr, c->partials); LAUNCHED(c);
     np = stats_allreduce(c, gv);
     k_epsilon_cell<<<vec_grid(c, n), kBlock, 0, c->stream>>>(n, ng, c->dm.cells, c->dm.last_cell, c->dm.xy, Rh, w,
                                                             c->partials, np, Cvel, Crv, eps);
@@ -224,11 +228,11 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
     double* beta = c->wk[9];
     if (variant == CFEM_EPS_LINEAR) {
       if (!w) CFEM_THROW(-1, "rv_epsilon(linear): velocity field w is required");
-      k_stats<-1><<<gv, kBlock, 0, c->stream>>>(n, nl, uh, nullptr, c->partials);
+      launch_pdl(k_stats<-1>, gv, kBlock, 0, c->stream, n, nl, uh, nullptr, c->partials);
     } else if (flux == CFEM_FLUX_BURGERS) {
-      k_stats<CFEM_FLUX_BURGERS><<<gv, kBlock, 0, c->stream>>>(n, nl, uh, beta, c->partials);
+      launch_pdl(k_stats<CFEM_FLUX_BURGERS>, gv, kBlock, 0, c->stream, n, nl, uh, beta, c->partials);
     } else if (flux == CFEM_FLUX_KPP) {
-      k_stats<CFEM_FLUX_KPP><<<gv, kBlock, 0, c->stream>>>(n, nl, uh, beta, c->partials);
+      launch_pdl(k_stats<CFEM_FLUX_KPP>, gv, kBlock, 0, c->stream, n, nl, uh, beta, c->partials);
     } else {
       CFEM_THROW(-1, "rv_epsilon(nonlinear): flux must be BURGERS or KPP");
     }
@@ -237,10 +241,10 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
     int64_t g = (int64_t)c->sm_count * 4;
     if (g > c->dm.ntiles) g = c->dm.ntiles;
     if (variant == CFEM_EPS_LINEAR)
-      k_epsilon_stream<true><<<(int)g, kTileNodes, 0, c->stream>>>(c->dm.ntiles, ng, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
+      launch_pdl(k_epsilon_stream<true>, (int)g, kTileNodes, 0, c->stream, c->dm.ntiles, ng, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
                                                                  u_n, Rh, nullptr, w, h, c->partials, np, Cvel, Crv, eps);
     else
-      k_epsilon_stream<false><<<(int)g, kTileNodes, 0, c->stream>>>(c->dm.ntiles, ng, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
+      launch_pdl(k_epsilon_stream<false>, (int)g, kTileNodes, 0, c->stream, c->dm.ntiles, ng, c->dm.tile_node, c->dm.rowptr, c->dm.colidx,
                                                                   u_n, Rh, beta, w, h, c->partials, np, Cvel, Crv, eps);
     LAUNCHED(c);
     halo_exchange(c, eps);
@@ -251,7 +255,7 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
     if (variant == CFEM_EPS_LINEAR_SIMPLE) {
       if (!u_n) CFEM_THROW(-1, "rv_epsilon(linear_simple): u_n is required");
       flux = CFEM_FLUX_ADVECTION;
-      k_stats<-1><<<gv, kBlock, 0, c->stream>>>(n, nl, u_n, nullptr, c->partials); LAUNCHED(c);
+      launch_pdl(k_stats<-1>, gv, kBlock, 0, c->stream, n, nl, u_n, nullptr, c->partials); LAUNCHED(c);
       np = stats_allreduce(c, gv);
     }
     if (flux == CFEM_FLUX_ADVECTION) {
