@@ -589,6 +589,7 @@ int cfem_state_set(cfem_ctx* c, const double* uh, const double* u_n, const doubl
   // iteration-count predictions restart with the state, so a run is a pure function of its inputs
   c->pcg_predict = 28;
   c->krylov_predict = 8;
+  c->dx_guess_valid = false;
   CUDA_OK(cudaStreamSynchronize(c->stream));
   API_END
 }
@@ -700,10 +701,21 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
     int it = 0;
     while (!converged && it < p->newton_max_it) {
       launch_cn_jacobian(c, p->flux, p->dt, c->uh, c->eps, J);
-      launch_fill(c, dx, 0.0, nn);
+      // The first Newton update of a step is close to the previous step's (the solution moves by nearly the
+      // same amount): start the Krylov solve from it.  The solve still runs to lin_rtol, so only the
+      // iteration count changes.  Later Newton iterations (tiny corrections) start from zero.
+      static const bool use_guess = !(getenv("CFEM_DXGUESS") && std::string(getenv("CFEM_DXGUESS")) == "0");
+      const bool guess = use_guess && it == 0 && c->dx_guess_valid;
+      if (guess) launch_copy(c, dx, c->dx_guess, nn);
+      else launch_fill(c, dx, 0.0, nn);
       SolveResult rk = run_solver(c, p->solver, J, F, dx, p->lin_rtol, 0.0, p->lin_max_it, &c->krylov_predict);
       if (!rk.converged) CFEM_THROW(-3, "step_scalar: Krylov solve did not converge (relres " + std::to_string(rk.relres) + ")");
       st.krylov_iterations += rk.iters;
+      if (use_guess && it == 0) {
+        if (!c->dx_guess) c->dx_guess = dalloc<double>(c, nn);
+        launch_copy(c, c->dx_guess, dx, nn);
+        c->dx_guess_valid = true;
+      }
       launch_sub(c, c->uh, dx, c->dm.no);
       halo_exchange(c, c->uh);
       ++it;

@@ -172,4 +172,6 @@ struct cfem_ctx {
   int64_t halo_exchanges = 0, allreduces = 0;
   cfem::Profiler prof;
   int pcg_predict = 28, krylov_predict = 8;
+  double* dx_guess = nullptr;   // first Newton update of the previous step (initial guess of the next Krylov solve)
+  bool dx_guess_valid = false;
 };
