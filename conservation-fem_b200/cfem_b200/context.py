@@ -25,6 +25,11 @@ def _field(a):
     return L.f64(a)
 
 
+class PatchDict(dict):
+    """``SI.get_patch_dictionary`` result that also knows the GPU context it came from."""
+    ctx = None
+
+
 class Context:
     """Everything the reference recomputes per step but that depends only on the mesh.
 
@@ -107,9 +112,16 @@ class Context:
         return self._pattern
 
     def patch_dictionary(self):
-        """dict node -> set(nodes) like ``SI.get_patch_dictionary`` (keys ascending)."""
+        """dict node -> set(nodes) like ``SI.get_patch_dictionary``, keys in the reference's insertion order
+        (first appearance of a dof when the cells are scanned in order, ``SI.py:18-26``) -- the order
+        ``helpers.smooth_vector`` sweeps in.  The dict remembers its context (``.ctx``)."""
         rowptr, colidx = self.csr_pattern()
-        return {int(i): set(colidx[rowptr[i]:rowptr[i + 1]].tolist()) for i in range(self.n)}
+        flat = np.asarray(self.cells).reshape(-1)
+        _, first = np.unique(flat, return_index=True)
+        keys = flat[np.sort(first)]
+        d = PatchDict((int(i), set(colidx[rowptr[i]:rowptr[i + 1]].tolist())) for i in keys)
+        d.ctx = self
+        return d
 
     def boundary_dofs(self):
         nb = self._lib.cfem_num_boundary(self._h)
@@ -259,6 +271,27 @@ class Context:
         bc_values = _field(bc_values)
         L.check(self._lib.cfem_step_scalar(self._h, C.byref(params), int(n_steps), L.ptr(bc_values), C.byref(st)))
         return st.as_dict()
+
+    def step_scalar_si(self, params: "L.StepParams", Cm, floor=1e-8, smooth_l=0.0, smooth_order=None, n_steps=1,
+                       bc_values=None):
+        """Smoothness-indicator stepper (``Exact_Burger_SI.py:159-197``); ``smooth_l`` > 0 applies
+        ``smooth_vector(uh, patches, smooth_l)`` after every Newton solve, sweeping in ``smooth_order``."""
+        st = L.StepStats()
+        bc_values = _field(bc_values)
+        order = None if smooth_order is None else np.ascontiguousarray(smooth_order, dtype=np.int32)
+        L.check(self._lib.cfem_step_scalar_si(self._h, C.byref(params), float(Cm), float(floor), float(smooth_l),
+                                              L.ptr(order), int(n_steps), L.ptr(bc_values), C.byref(st)))
+        return st.as_dict()
+
+    def smooth_vector(self, u, l, order=None):
+        """``helpers.smooth_vector`` in place on ``u`` (numpy array or dolfinx-like Function); ``order``: caller
+        dof ids in sweep order (None = ascending)."""
+        a = _field(u)
+        order = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+        if order is not None and order.size != self.n:
+            raise ValueError("smooth_vector: order must list every dof once")
+        L.check(self._lib.cfem_smooth_vector(self._h, L.ptr(a), L.ptr(order), float(l)))
+        return a
 
     def step_advection(self, params: "L.StepParams", n_steps=1, first_gfem=False):
         st = L.StepStats()

@@ -125,6 +125,36 @@ def solve_burgers(domain, initial_condition=burgers_initial_condition, dt=None, 
                        scheme, newton_rtol, solver, lin_rtol, device, h, return_stats)
 
 
+def solve_burgers_si(domain, initial_condition=burgers_initial_condition, dt=None, num_steps=None, Cm=0.5,
+                     floor=1e-8, smooth_l=4.0, CFL=0.5, T=0.5, newton_rtol=1e-4, solver="bicgstab", lin_rtol=1e-13,
+                     device=0, h=None, return_stats=False):
+    """Burgers with the smoothness-indicator viscosity and the ``smooth_vector`` post-filter
+    (``Code/Burgers_equation/Exact_Burger_SI.py:159-197``); ``smooth_l=0`` skips the filter.  The filter sweeps
+    the nodes in the key order of ``SI.get_patch_dictionary`` like the reference."""
+    ctx = domain if isinstance(domain, Context) else Context.for_domain(domain, device=device)
+    h = ctx.nodal_h() if h is None else _interpolate(ctx, h)
+    if dt is None:
+        dt = CFL * float(np.min(h))
+    if num_steps is None:
+        num_steps = int(np.ceil(T / dt))
+    u0 = _interpolate(ctx, initial_condition)
+    ctx.state_set(uh=u0, u_n=u0, u_old=u0, u_oo=u0, RH=np.zeros(ctx.n), h=h, t=0.0)
+    p = step_params(L.FLUX_BURGERS, dt, 0.0, 0.0, newton_rtol=newton_rtol, solver=solver, lin_rtol=lin_rtol,
+                    bc_kind="burgers_exact")
+    order = None
+    if smooth_l:
+        flat = np.asarray(ctx.cells).reshape(-1)
+        _, first = np.unique(flat, return_index=True)
+        order = flat[np.sort(first)].astype(np.int32)      # first appearance over the cells, SI.py:18-26
+    stats = ctx.step_scalar_si(p, Cm, floor, smooth_l=smooth_l, smooth_order=order, n_steps=num_steps)
+    out = ctx.state_get(("uh", "eps"))
+    uh = NodalFunction(out["uh"], "uh")
+    if return_stats:
+        stats["eps"], stats["h"] = out["eps"], h
+        return uh, stats
+    return uh
+
+
 def solve_advection(domain, initial_condition=advection_initial_condition, velocity=advection_velocity, dt=None,
                     num_steps=None, hmax=None, Cvel=0.25, Crv=1.0, CFL=0.5, T=1.0, residual_bc=False,
                     solver="bicgstab", lin_rtol=1e-13, device=0, h=None, return_stats=False):

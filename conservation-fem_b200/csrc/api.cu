@@ -351,6 +351,7 @@ void cfem_destroy(cfem_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   for (cudaEvent_t e : c->prof.ev) cudaEventDestroy(e);
   euler_free(c);
+  smooth_plan_free(c);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -654,8 +655,12 @@ static double partials_norm(cfem_ctx* c, double* part, int npart) {
   return sqrt(s);
 }
 
-int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const double* bc_values,
-                     cfem_step_stats* stats) {
+// smoothness-indicator variant of the scalar stepper (Exact_Burger_SI.py:159-197): SI viscosity instead of the
+// residual projection + RV formula, optional smooth_vector post-filter after the Newton solve
+struct SiOptions { double Cm, floor; double smooth_l; const int32_t* smooth_order; };
+
+static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps, const double* bc_values,
+                            cfem_step_stats* stats, const SiOptions* si) {
   API_BEGIN
   CUDA_OK(cudaSetDevice(c->device));
   if (!p) CFEM_THROW(-1, "step_scalar: null params");
@@ -686,15 +691,27 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
   for (int s = 0; s < n_steps; ++s) {
     c->t += p->dt;
     launch_bc_values(c, p->bc_kind, p->bc_value, c->t, d_bc_user ? d_bc_user + (int64_t)s * c->nbc_user : nullptr, c->g);
-    // (a-3) residual projection  M_bc RH = b
-    launch_rv_rhs(c, p->flux, p->scheme, p->dt, c->u_n, c->u_old, c->u_oo, nullptr, true, b, c->fluxn);
-    SolveResult rm = mass_solve(c, p->mass_solver, c->mat[CFEM_MAT_MASS_BC], b, c->RH, p->lin_rtol, p->lin_max_it, &c->pcg_predict);
-    if (!rm.converged) CFEM_THROW(-3, "step_scalar: residual PCG did not converge");
-    st.mass_iterations += rm.iters;
-    // (a-4) nodal viscosity
-    launch_epsilon(c, CFEM_EPS_NONLINEAR, p->flux, p->Cvel, p->Crv, c->uh, c->u_n, c->RH, c->h, nullptr, c->eps);
+    const double* fluxn = nullptr;
+    if (!si) {
+      // (a-3) residual projection  M_bc RH = b
+      launch_rv_rhs(c, p->flux, p->scheme, p->dt, c->u_n, c->u_old, c->u_oo, nullptr, true, b, c->fluxn);
+      fluxn = c->fluxn;
+      SolveResult rm = mass_solve(c, p->mass_solver, c->mat[CFEM_MAT_MASS_BC], b, c->RH, p->lin_rtol, p->lin_max_it, &c->pcg_predict);
+      if (!rm.converged) CFEM_THROW(-3, "step_scalar: residual PCG did not converge");
+      st.mass_iterations += rm.iters;
+      // (a-4) nodal viscosity
+      launch_epsilon(c, CFEM_EPS_NONLINEAR, p->flux, p->Cvel, p->Crv, c->uh, c->u_n, c->RH, c->h, nullptr, c->eps);
+    } else {
+      // (f-1) smoothness-indicator viscosity from the bc'd unit stiffness matrix (Exact_Burger_SI.py:169-174)
+      if (!c->unit_stiffness.vals) {
+        c->unit_stiffness.vals = dalloc<double>(c, c->dm.nnz + 8);
+        c->unit_stiffness.dinv = dalloc<double>(c, c->dm.nn);
+      }
+      if (!c->unit_stiffness.valid) launch_stiffness(c, c->unit_stiffness, nullptr);
+      launch_si_epsilon(c, p->flux, si->Cm, si->floor, true, c->unit_stiffness, c->u_n, c->h, nullptr, nullptr, c->eps);
+    }
     // (a-8) Newton on the Crank-Nicolson residual, dolfinx NewtonSolver 'residual' criterion
-    int np = launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, c->fluxn, F, normpart);
+    int np = launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, fluxn, F, normpart);
     double res = partials_norm(c, normpart, np);
     const double res0 = res;
     bool converged = res < p->newton_atol;
@@ -719,13 +736,14 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
       launch_sub(c, c->uh, dx, c->dm.no);
       halo_exchange(c, c->uh);
       ++it;
-      np = launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, c->fluxn, F, normpart);
+      np = launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, fluxn, F, normpart);
       res = partials_norm(c, normpart, np);
       converged = (res / res0 < p->newton_rtol) || (res < p->newton_atol);
     }
     st.newton_iterations += it;
     st.last_newton_residual = res;
     if (!converged) CFEM_THROW(-3, "Newton solver did not converge in " + std::to_string(it) + " iterations");
+    if (si && si->smooth_l > 0.0) launch_smooth_vector(c, c->uh, si->smooth_order, si->smooth_l);  // helpers.py:40-50
     // rotate  u_oo <- u_old <- u_n <- uh   (KPP_exact.py:159-161)
     double* tmp = c->u_oo;
     c->u_oo = c->u_old;
@@ -746,6 +764,29 @@ int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const 
   st.spmv_launches = c->launches.spmv - l0.spmv;
   st.assembly_launches = c->launches.assembly - l0.assembly;
   if (stats) *stats = st;
+  API_END
+}
+
+int cfem_step_scalar(cfem_ctx* c, const cfem_step_params* p, int n_steps, const double* bc_values,
+                     cfem_step_stats* stats) {
+  return step_scalar_impl(c, p, n_steps, bc_values, stats, nullptr);
+}
+
+int cfem_step_scalar_si(cfem_ctx* c, const cfem_step_params* p, double Cm, double floor_, double smooth_l,
+                        const int32_t* smooth_order, int n_steps, const double* bc_values, cfem_step_stats* stats) {
+  const SiOptions si{Cm, floor_, smooth_l, smooth_order};
+  return step_scalar_impl(c, p, n_steps, bc_values, stats, &si);
+}
+
+int cfem_smooth_vector(cfem_ctx* c, double* u_io, const int32_t* order, double l) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!u_io) CFEM_THROW(-1, "smooth_vector: null field");
+  double* u = c->wk[9];
+  import_vec(c, u_io, u);
+  launch_smooth_vector(c, u, order, l);
+  export_vec(c, u, u_io);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
   API_END
 }
 

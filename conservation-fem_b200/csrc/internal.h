@@ -142,6 +142,7 @@ struct cfem_ctx {
   std::vector<int32_t> bc_user;   // caller's Dirichlet set
   cfem::Matrix mat[4];
   cfem::Matrix unit_stiffness;      // int grad u . grad v, assembled on first use (SI viscosity)
+  void* smooth_plan = nullptr;      // level schedule of the last smooth_vector order (smooth.cu)
   // state vectors (internal order)
   double *uh = nullptr, *u_n = nullptr, *u_old = nullptr, *u_oo = nullptr, *RH = nullptr,
          *eps = nullptr, *h = nullptr, *g = nullptr, *fluxn = nullptr;

@@ -29,6 +29,11 @@ int assembly_grid(const cfem_ctx* c);
 void launch_grad_matrix(cfem_ctx* c, int d, Matrix& C);                                  // int phi_a d_d phi_b
 void launch_mass_stiff(cfem_ctx* c, const double* eps, double coef, Matrix& S);          // M + coef K_eps
 
+// ---- smooth_vector post-filter (smooth.cu) -------------------------------------
+// in-place sweep over u (internal numbering) in the caller's order (host array of caller dof ids, or null = ascending)
+void launch_smooth_vector(cfem_ctx* c, double* u, const int32_t* order_host, double l);
+void smooth_plan_free(cfem_ctx* c);
+
 // ---- linear algebra (linalg.cu) ------------------------------------------------
 void launch_spmv(cfem_ctx* c, const Matrix& A, const double* x, double* y);
 void launch_gather(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n);      // dst[i] = src[idx[i]]

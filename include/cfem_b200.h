@@ -229,6 +229,20 @@ int cfem_step_scalar(cfem_ctx* ctx, const cfem_step_params* p, int n_steps,
                      const double* bc_values, cfem_step_stats* stats);
 /* Linear advection: first_gfem != 0 does the plain CN step of
  * RV_node.py:140-157 first; then RV steps of RV_node.py:206-251. */
+/* ---- (f-1, f-4) smoothness-indicator stepper + smooth_vector post-filter --------------------------------
+ * cfem_step_scalar_si: the loop body of Code/Burgers_equation/Exact_Burger_SI.py:159-197 -- per step the SI
+ * viscosity eps = psi(alpha) Cm h ||f'(u_n)|| from the bc'd unit stiffness matrix (SI.py:38-67), the same
+ * Crank-Nicolson Newton solve as cfem_step_scalar, then (smooth_l > 0) helpers.smooth_vector(uh, patches,
+ * smooth_l) before the rotation.  Cvel / Crv / scheme of the params are unused.
+ * cfem_smooth_vector: helpers.smooth_vector (helpers.py:40-50) on its own, in place on u_io (caller numbering):
+ * an in-place sweep, node after node in `order` (caller dof ids in sweep order -- the key order of the
+ * reference's patches dict; NULL = ascending), each node seeing the already smoothed values of the neighbours
+ * that precede it.  Run on the device level by level (exactly the sequential result up to the order of the
+ * additions inside one patch sum).  Single-GPU contexts only. */
+int cfem_step_scalar_si(cfem_ctx* ctx, const cfem_step_params* p, double Cm, double floor, double smooth_l,
+                        const int32_t* smooth_order, int n_steps, const double* bc_values, cfem_step_stats* stats);
+int cfem_smooth_vector(cfem_ctx* ctx, double* u_io, const int32_t* order, double l);
+
 int cfem_step_advection(cfem_ctx* ctx, const cfem_step_params* p, int n_steps, int first_gfem,
                         cfem_step_stats* stats);
 

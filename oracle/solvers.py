@@ -338,6 +338,34 @@ def run_burgers(x, cells, dt, num_steps, Cvel=0.5, Crv=10.0, **kw):
                       lambda t: burgers_exact(x[bnd], t), newton_rtol=1e-4, **kw)
 
 
+def run_burgers_si(x, cells, dt, num_steps, Cm=0.5, floor=1e-8, smooth_l=4.0):
+    """``Code/Burgers_equation/Exact_Burger_SI.py:159-197``: per step the SI viscosity from the bc'd unit
+    stiffness matrix and ``u_n`` (``SI.py:38-67``), the Crank-Nicolson Newton solve with exact Dirichlet data,
+    then ``smooth_vector(uh, node_patches, l)`` (literal in-place sweep in the patches' key order;
+    ``smooth_l = 0`` skips it)."""
+    x = np.asarray(x, dtype=np.float64)
+    m = Mesh(x, cells)
+    h = p1.nodal_h(m.x, m.cells)
+    K = p1.stiffness_matrix(m.x, m.cells)
+    patches = p1.node_patches(m.cells)
+    uh = burgers_initial_condition(x)
+    u_n = uh.copy()
+    t, its_all = 0.0, []
+    for _ in range(num_steps):
+        t += dt
+        g = burgers_exact(x[m.bnd], t)
+        eps, _ = rv.si_epsilon(K, u_n, h, rv.beta_burgers(u_n), Cm, floor, bc_nodes=m.bnd)
+        un = u_n
+        uh, its = newton(lambda u: cn_residual("burgers", m, dt, u, un, eps),
+                         lambda u: cn_jacobian("burgers", m, dt, u, eps),
+                         uh, m.bnd, g, rtol=1e-4, max_it=100)
+        its_all.append(its)
+        if smooth_l:
+            rv.smooth_vector_literal(uh, patches, smooth_l)
+        u_n = uh.copy()
+    return uh, eps, its_all, m, h
+
+
 # --------------------------------------------------------------- linear advection
 
 

@@ -197,6 +197,59 @@ def test_krylov_vs_lu(case, solver):
     assert ctx.last_relres <= 1e-13
 
 
+def test_patch_dictionary_key_order(case):
+    """keys in the reference's insertion order (first appearance over the cell loop, SI.py:18-26)."""
+    _, x, c, ctx, m = case
+    got = ctx.patch_dictionary()
+    assert list(got.keys()) == list(p1.node_patches(c).keys()) and got.ctx is ctx
+
+
+@pytest.mark.parametrize("order_kind", ["patches", "ascending", "random"])
+def test_smooth_vector_matches_sequential_sweep(case, order_kind):
+    """helpers.smooth_vector (helpers.py:40-50) is an in-place, order-dependent sweep; the level-scheduled
+    device version must reproduce the literal loop for any sweep order.  Tolerance 1e-13: only the order of the
+    <= 8 additions inside one patch sum differs (the reference leaves it to Python's set iteration)."""
+    _, x, c, ctx, m = case
+    uh, *_ = fields(m, seed=3)
+    patches = p1.node_patches(c)
+    if order_kind == "ascending":
+        patches = {k: patches[k] for k in sorted(patches)}
+    elif order_kind == "random":
+        keys = np.random.default_rng(1).permutation(m.n)
+        patches = {int(k): patches[int(k)] for k in keys}
+    for l in (4.0, 6.0):
+        ref = rv.smooth_vector_literal(uh.copy(), patches, l)
+        got = uh.copy()
+        order = None if order_kind == "ascending" else np.fromiter(patches.keys(), dtype=np.int32)
+        ctx.smooth_vector(got, l, order=order)
+        assert rel(got, ref) < 1e-13
+        assert rel(got, uh) > 1e-3          # it did something
+        # and it is NOT the Jacobi (all-old-values) version: the sweep order matters
+        jac = uh.copy()
+        for i, adj in patches.items():
+            d = len(adj) - 1
+            jac[i] = (sum(uh[j] for j in adj if j != i) + (l - 1) * d * uh[i]) / (l * d)
+        if m.n > 3:
+            assert rel(got, jac) > 1e-6
+
+
+def test_smooth_vector_shim_and_bad_order(case):
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "conservation-fem_b200"))
+    from Utils.helpers import smooth_vector
+    from Utils.SI import SI
+
+    _, x, c, ctx, m = case
+    uh, *_ = fields(m, seed=4)
+    patches = SI(1, ctx, 1e-8).get_patch_dictionary()
+    f = GS.NodalFunction(uh.copy())
+    smooth_vector(f, patches, 4)
+    assert rel(f.x.array, rv.smooth_vector_literal(uh.copy(), p1.node_patches(c), 4)) < 1e-13
+    with pytest.raises(L.CfemError, match="permutation|range"):
+        ctx.smooth_vector(uh.copy(), 4.0, order=np.zeros(m.n, dtype=np.int32) if m.n > 1 else np.array([5], dtype=np.int32))
+
+
 def test_owned_layout_state_roundtrip(case):
     """cfem_state_update_owned / cfem_state_get_owned: entry i is caller dof ordering[i] (all dofs on one GPU)."""
     _, x, c, ctx, m = case
@@ -256,6 +309,23 @@ def test_burgers_steps(solver):
     assert rel(uh.x.array, st.uh) < TOL_FIELD
     assert stats["newton_iterations"] == sum(st.newton_its)
     assert rel(stats["eps"], st.eps) < 1e-8
+
+
+@pytest.mark.parametrize("smooth_l", [0.0, 4.0])
+def test_burgers_si_steps(smooth_l):
+    """Exact_Burger_SI.py loop: SI viscosity + CN Newton (+ smooth_vector l=4, Exact_Burger_SI.py:193)."""
+    x, c = meshes.jittered(36, 36) if smooth_l else meshes.rectangle(40, 40)
+    dt, n = 0.5 / 40, 10
+    uh_ref, eps_ref, its, m, h = S.run_burgers_si(x, c, dt, n, smooth_l=smooth_l)
+    # the SI viscosity vanishes in smooth regions (nearly Galerkin, worse conditioned than the RV systems):
+    # Krylov solves to 1e-14 keep the LU-based oracle within the 1e-10 bar (2e-10 at 1e-13)
+    uh, stats = GS.solve_burgers_si((x, c), dt=dt, num_steps=n, smooth_l=smooth_l, lin_rtol=1e-14, return_stats=True)
+    assert rel(uh.x.array, uh_ref) < TOL_FIELD
+    assert stats["newton_iterations"] == sum(its)
+    # alpha = |sum k_ij du| / sum |k_ij||du| cancels heavily where u is nearly flat: the 1e-10 field
+    # difference of the previous step shows up as ~1e-6 in eps (in the oracle a random 1e-10 perturbation of u_n
+    # moves eps by 1e-2: flat regions divide round-off by the 1e-8 floor)
+    assert rel(stats["eps"], eps_ref) < 1e-4
 
 
 def test_kpp_steps_unstructured():
