@@ -222,6 +222,33 @@ def solve_euler(domain, initial_condition=sod_initial_condition, dt=None, num_st
     return out["Uh"]
 
 
+def solve_advection_rk4(domain, initial_condition=advection_initial_condition, velocity=advection_velocity, dt=None,
+                        num_steps=None, hmax=None, CFL=0.5, T=1.0, lin_rtol=1e-14, device=0):
+    """Galerkin linear advection with classical RK4 (``Code/Linear_advection/GFEM_RK4.py:134-218``).  Every stage
+    is one residual projection on the GPU: ``k = -M_bc^{-1} int (w . grad u) v`` is ``cfem_rv_residual`` with a
+    vanishing time-derivative term (``u_old = u_n``) and Dirichlet rows (``GFEM_RK4.py:127-131``)."""
+    ctx = domain if isinstance(domain, Context) else Context.for_domain(domain, device=device)
+    u = _interpolate(ctx, initial_condition).copy()
+    w = _interpolate(ctx, velocity)
+    if dt is None:
+        dt = advection_dt(w, hmax, CFL)
+    if num_steps is None:
+        num_steps = int(np.ceil(T / dt))
+
+    def k_of(v, guess):
+        return -ctx.rv_residual("advection", "bdf1", dt, v, v, w=w, use_bc=True, R0=guess, rtol=lin_rtol)
+
+    g = np.zeros(ctx.n)
+    for _ in range(num_steps):
+        k1 = k_of(u, g)
+        k2 = k_of(u + 0.5 * dt * k1, -k1)
+        k3 = k_of(u + 0.5 * dt * k2, -k2)
+        k4 = k_of(u + dt * k3, -k3)
+        u += (dt / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+        g = -k4
+    return NodalFunction(u, "u_n")
+
+
 # ---- (f-2) L2-error functional and convergence-rate fit -------------------------------------------------
 def l2_error(domain, uh, u_ref):
     """``sqrt(assemble_scalar((uh - u_ref)**2 * dx))`` with both fields in P1 (mass-matrix norm on the GPU).

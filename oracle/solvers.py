@@ -419,6 +419,30 @@ def run_advection(x, cells, dt, num_steps, Cvel=0.25, Crv=1.0, u0=None, w=None, 
     return uh, eps, m, h
 
 
+def run_advection_rk4(x, cells, dt, num_steps, u0=None, w=None):
+    """``Code/Linear_advection/GFEM_RK4.py:134-218``: Galerkin linear advection, classical RK4 in time; every
+    stage solves ``M_bc k = -int (w . grad u) v`` with homogeneous Dirichlet rows (LU in the reference)."""
+    x = np.asarray(x, dtype=np.float64)
+    m = Mesh(x, cells)
+    u = advection_initial_condition(x) if u0 is None else np.array(u0, dtype=np.float64)
+    w = advection_velocity(x) if w is None else w
+    C = p1.assemble_matrix(m.cells, p1.convection_elements(m.area, m.grad, np.asarray(w).reshape(-1, 2)[m.cells]), m.n)
+    lu = splu(p1.apply_bc_matrix(m.M, m.bnd).tocsc())
+
+    def k_of(v):
+        b = -(C @ v)
+        b[m.bnd] = 0.0
+        return lu.solve(b)
+
+    for _ in range(num_steps):
+        k1 = k_of(u)
+        k2 = k_of(u + 0.5 * dt * k1)
+        k3 = k_of(u + 0.5 * dt * k2)
+        k4 = k_of(u + dt * k3)
+        u = u + (dt / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+    return u, m
+
+
 # ------------------------------------------------------------------ functionals
 
 

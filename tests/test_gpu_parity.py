@@ -328,6 +328,16 @@ def test_burgers_si_steps(smooth_l):
     assert rel(stats["eps"], eps_ref) < 1e-4
 
 
+def test_advection_rk4_steps():
+    """GFEM_RK4.py:134-218, four mass solves per step."""
+    x, c = meshes.jittered(30, 30, (-1, -1), (1, 1))
+    dt = S.advection_dt(S.advection_velocity(x), 1 / 15)
+    ref, m = S.run_advection_rk4(x, c, dt, 8)
+    uh = GS.solve_advection_rk4((x, c), dt=dt, num_steps=8)
+    assert rel(uh.x.array, ref) < TOL_FIELD
+    assert rel(uh.x.array, S.advection_initial_condition(x)) > 1e-2
+
+
 def test_kpp_steps_unstructured():
     x, c = meshes.jittered(40, 40, (-2, -2), (2, 2))
     dt, n = 0.64 * 4 / 40, 10
