@@ -1,7 +1,7 @@
 """Regenerates the fixtures in tests/golden/ (run in the authoring container only).
 
-1. Meshes lifted from the reference's own data files (contiguous HDF5 datasets read by
-   byte offset, h5py is not available; offsets documented in SURVEY.md section 4):
+1. Meshes lifted from the reference's own data files (read with cfem_b200.io.H5File, a reader for
+   the HDF5 subset dolfinx writes; h5py is not available):
      Code/Linear_advection/Data/RV/RV_node.h5  -> rv_node_mesh.npz  (1,919 tris / 1,011 nodes, unit disk)
      Data/KPP_RV.h5                            -> kpp_rv_mesh.npz   (9,514 tris / 4,886 nodes, [-2,2]^2)
    plus the first <Time> stamp of RV_node.xdmf, which pins the reference's dt formula.
@@ -9,15 +9,14 @@
      Code/Linear_advection/Data/RV/RV_node.h5   (tests/eps_func.py)                 -> ref_series_eps_func.npz
      Code/Linear_advection/Data/RV/RV_cell.h5   (Code/Linear_advection/RV_cell.py)  -> ref_series_rv_cell.npz
      Code/Linear_advection/Data/SI/smoothness.h5 (smoothness_old_convergence.py loop) -> ref_series_si_old.npz
-   (datasets located through their HDF5 data-layout messages; 13 of the 285 frames are kept, the
-   generator checks all 285 against the oracle).  These ARE dolfinx output: they pin the oracle.
+   (read through cfem_b200.io.read_xdmf; 13 of the 285 frames are kept, the generator checks all 285
+   against the oracle).  These ARE dolfinx output: they pin the oracle.
 3. Oracle outputs on small seeded cases (fields after N steps), so GPU parity can also be
    checked against committed vectors.  These come from oracle/ (CPU restatement): the reference
    itself cannot run in this image (no dolfinx).
 """
 import os
 import re
-import struct
 import sys
 
 import numpy as np
@@ -29,34 +28,6 @@ sys.path.insert(0, os.path.join(ROOT, "conservation-fem_b200"))
 REF = "/root/reference"
 
 
-def read_mesh(path, n_cells, n_nodes, topo_off, geom_off):
-    raw = open(path, "rb").read()
-    cells = np.frombuffer(raw, dtype="<i8", count=3 * n_cells, offset=topo_off).reshape(-1, 3)
-    if geom_off < 0:
-        geom_off = len(raw) + geom_off
-    x = np.frombuffer(raw, dtype="<f8", count=2 * n_nodes, offset=geom_off).reshape(-1, 2)
-    assert cells.min() == 0 and cells.max() == n_nodes - 1
-    return x.copy(), cells.astype(np.int32)
-
-
-def contiguous_datasets(raw, nbytes):
-    """File addresses of the contiguous HDF5 datasets of exactly ``nbytes`` (data layout message
-    version 3, class 1: ``03 01 <address:8> <size:8>``), in file (= creation = time) order."""
-    out = []
-    for mt in re.finditer(re.escape(struct.pack("<Q", nbytes)), raw):
-        p = mt.start()
-        a = struct.unpack("<Q", raw[p - 8:p])[0]
-        if raw[p - 10:p - 8] == b"\x03\x01" and 0 < a <= len(raw) - nbytes:
-            out.append(a)
-    return sorted(out)
-
-
-def read_series(path, n_nodes):
-    raw = open(path, "rb").read()
-    return np.array([np.frombuffer(raw, dtype="<f8", count=n_nodes, offset=a)
-                     for a in contiguous_datasets(raw, 8 * n_nodes)])
-
-
 KEEP = [0, 1, 2, 3, 5, 10, 20, 50, 100, 150, 200, 250, 284]
 SERIES = {"eps_func": "Code/Linear_advection/Data/RV/RV_node.h5",
           "rv_cell": "Code/Linear_advection/Data/RV/RV_cell.h5",
@@ -64,10 +35,11 @@ SERIES = {"eps_func": "Code/Linear_advection/Data/RV/RV_node.h5",
 
 
 def stored_series(S, x, c):
+    from cfem_b200 import io
     for variant, rel in SERIES.items():
-        F = read_series(f"{REF}/{rel}", len(x))
-        xdmf = open(f"{REF}/{rel}".replace(".h5", ".xdmf")).read()
-        times = np.array([float(t) for t in re.findall(r'<Time Value="([0-9.eE+-]+)"', xdmf)])
+        d = io.read_xdmf(f"{REF}/{rel}".replace(".h5", ".xdmf"))
+        assert np.array_equal(d["x"], x) and np.array_equal(d["cells"], c)
+        times, F = d["series"]["uh"]
         assert F.shape == (285, len(x)) and len(times) == 285
         U, _, dt = S.run_advection_stored(x, c, variant)
         err = np.linalg.norm(U - F, axis=1) / np.linalg.norm(F, axis=1)
@@ -79,16 +51,16 @@ def stored_series(S, x, c):
 
 def main():
     from oracle import p1, solvers as S
-    from cfem_b200 import meshes
+    from cfem_b200 import io, meshes
 
-    x, c = read_mesh(f"{REF}/Code/Linear_advection/Data/RV/RV_node.h5", 1919, 1011, 3464, 51568)
+    x, c = io.read_mesh(f"{REF}/Code/Linear_advection/Data/RV/RV_node.h5")
     area, _ = p1.cell_geometry(x, c)
     assert abs(area.sum() - np.pi) < 5e-3 and np.all(area > 0)
     xdmf = open(f"{REF}/Code/Linear_advection/Data/RV/RV_node.xdmf").read()
     t0 = re.search(r'<Time Value="([0-9.eE+-]+)"', xdmf).group(1)
     np.savez_compressed(f"{HERE}/rv_node_mesh.npz", x=x, cells=c, first_time_stamp=np.array(float(t0)),
                         first_time_stamp_text=np.array(t0))
-    x, c = read_mesh(f"{REF}/Data/KPP_RV.h5", 9514, 4886, 3464, -78176)
+    x, c = io.read_mesh(f"{REF}/Data/KPP_RV.h5")
     area, _ = p1.cell_geometry(x, c)
     assert abs(area.sum() - 16.0) < 1e-9 and np.all(area > 0)
     np.savez_compressed(f"{HERE}/kpp_rv_mesh.npz", x=x, cells=c)

@@ -338,6 +338,23 @@ def test_advection_rk4_steps():
     assert rel(uh.x.array, S.advection_initial_condition(x)) > 1e-2
 
 
+def test_solver_writes_xdmf_series(tmp_path):
+    """KPP_exact.py:108-109,165: write_mesh + write_function(uh, t) from inside the loop."""
+    from cfem_b200 import io
+
+    x, c = meshes.rectangle(24, 24)
+    dt = 0.5 / 24
+    ref = GS.solve_burgers((x, c), dt=dt, num_steps=7)
+    path = str(tmp_path / "burgers.xdmf")
+    uh, st = GS.solve_burgers((x, c), dt=dt, num_steps=7, xdmf=path, write_every=3, return_stats=True)
+    assert st["steps"] == 7 and rel(uh.x.array, ref.x.array) < 1e-12
+    d = io.read_xdmf(path)
+    t, F = d["series"]["uh"]
+    assert np.array_equal(d["x"], x) and np.array_equal(d["cells"], c)
+    assert F.shape == (3, x.shape[0]) and np.allclose(t, [3 * dt, 6 * dt, 7 * dt], rtol=1e-14)
+    assert np.array_equal(F[-1], uh.x.array)
+
+
 def test_kpp_steps_unstructured():
     x, c = meshes.jittered(40, 40, (-2, -2), (2, 2))
     dt, n = 0.64 * 4 / 40, 10
