@@ -312,6 +312,9 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic,
                 "algorithmic_bytes_per_launch": kinds[dom][1], "avg_launch_ms": dom_ms,
+                "timing": ("CUDA events on the context stream around each run of back-to-back k_cheb_stream launches of a "
+                           "mass solve (one event pair per run, divided by its launch count); per-launch event pairs "
+                           "for the other kernels") if dom == "chebyshev" else "one CUDA-event pair per launch on the context stream",
                 "launches": prof[dom]["launches"],
                 "share_of_step": prof[dom]["ms"] / total_prof_ms if total_prof_ms else None,
                 "spmv_type_share_of_step": (prof["spmv"]["ms"] + prof["chebyshev"]["ms"]) / total_prof_ms if total_prof_ms else None,

@@ -14,7 +14,7 @@ namespace cfem {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
-ProfScope::ProfScope(cfem_ctx* c_, int cat) : c(c_), active(false) {
+ProfScope::ProfScope(cfem_ctx* c_, int cat, int launches) : c(c_), active(false) {
   Profiler& p = c->prof;
   if (!p.on) return;
   if (p.depth++ > 0) return;  // nested scopes are charged to the outermost category
@@ -23,6 +23,7 @@ ProfScope::ProfScope(cfem_ctx* c_, int cat) : c(c_), active(false) {
   idx = p.used;
   p.used += 2;
   p.cat[idx / 2] = cat;
+  p.weight[idx / 2] = launches;
   cudaEventRecord(p.ev[idx], c->stream);
 }
 ProfScope::~ProfScope() {
@@ -860,6 +861,7 @@ int cfem_profile_begin(cfem_ctx* c, int max_launches) {
     p.ev.push_back(e);
   }
   p.cat.assign(p.ev.size() / 2, 0);
+  p.weight.assign(p.ev.size() / 2, 1);
   p.used = 0;
   p.depth = 0;
   p.on = true;
@@ -877,7 +879,7 @@ int cfem_profile_end(cfem_ctx* c, double* ms_per_category, int64_t* launches_per
     float ms = 0.f;
     CUDA_OK(cudaEventElapsedTime(&ms, p.ev[e], p.ev[e + 1]));
     ms_per_category[p.cat[e / 2]] += ms;
-    launches_per_category[p.cat[e / 2]] += 1;
+    launches_per_category[p.cat[e / 2]] += p.weight[e / 2];
   }
   p.used = 0;
   API_END

@@ -108,6 +108,7 @@ struct Profiler {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs
   std::vector<int> cat;
+  std::vector<int> weight;       // kernel launches a scope stands for (a chain timed as a whole)
   size_t used = 0;               // events used
   int depth = 0;                 // nesting depth of live scopes
 };
@@ -119,7 +120,7 @@ namespace cfem {
 // RAII: brackets the launches issued inside its scope with two events when profiling is on.
 struct ProfScope {
   cfem_ctx* c; bool active; size_t idx = 0;
-  ProfScope(cfem_ctx* c, int cat);
+  ProfScope(cfem_ctx* c, int cat, int launches = 1);
   ~ProfScope();
 };
 }  // namespace cfem

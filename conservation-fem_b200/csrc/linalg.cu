@@ -558,6 +558,10 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
   if (target < 2) target = 2;
   if (target > max_it) target = max_it;
   while (true) {
+    // the iterations up to the next check are timed as ONE scope of (target - it) launches: the per-launch
+    // figure then is the in-situ one (back-to-back launches, programmatic dependent launch active)
+    {
+    ProfScope chain(c, PROF_CHEB, target - it);
     for (; it < target; ++it) {
       const GhostSrc gsrc = halo_push(c, xa, false, !g_spmv_tma);
       ProfScope ps(c, PROF_CHEB);
@@ -585,6 +589,7 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
       c->launches.spmv++;
       if (it == 0) np_bb = allreduce_sum1(c, part + P_BB * kMaxPartials, gs);
       std::swap(xa, xb);
+    }
     }
     // the last kernel measured ||b - M x_{it-1}||; x_it is one update further on
     const int np_rr = allreduce_sum1(c, part + P_RR * kMaxPartials, gs);
