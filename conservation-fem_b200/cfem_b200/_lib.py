@@ -161,11 +161,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("CFEM_LIB", LIB_PATH)   # CFEM_LIB: an alternative build of the same ABI (kernel A/B runs)
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make -C conservation-fem_b200/csrc`). cfem_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
