@@ -37,6 +37,25 @@ def local_mass_rows(x, hm):
 @pytest.mark.parametrize("mesh", ["rect", "jittered"])
 def test_partition_consistency(world, mesh):
     x, c = meshes.rectangle(24, 17) if mesh == "rect" else meshes.jittered(21, 19)
+    check_partition(x, c, world)
+
+
+def test_partition_consistency_random_meshes():
+    """Property test: unstructured Delaunay meshes with random node / cell numbering, random world sizes
+    (ragged partitions, ranks whose range is a handful of nodes)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=12, deadline=None, derandomize=True)
+    @given(st.integers(40, 400), st.integers(1, 9), st.integers(0, 10 ** 6))
+    def run(npts, world, seed):
+        x, c = meshes.delaunay(npts, seed=seed % 1000)
+        x, c = meshes.permuted(x, c, np.random.default_rng(seed))
+        check_partition(x, c, world)
+
+    run()
+
+
+def check_partition(x, c, world):
     nn = x.shape[0]
     parts = [L.host_analyse(x, c, rank=r, world=world) for r in range(world)]
     owned = [p["n2u"][: p["n_owned"]] for p in parts]
