@@ -279,6 +279,8 @@ class Context:
         st = L.StepStats()
         bc_values = _field(bc_values)
         order = None if smooth_order is None else np.ascontiguousarray(smooth_order, dtype=np.int32)
+        if order is not None and order.size != self.n:
+            raise ValueError("step_scalar_si: smooth_order must list every dof once")
         L.check(self._lib.cfem_step_scalar_si(self._h, C.byref(params), float(Cm), float(floor), float(smooth_l),
                                               L.ptr(order), int(n_steps), L.ptr(bc_values), C.byref(st)))
         return st.as_dict()
