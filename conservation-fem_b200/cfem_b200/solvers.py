@@ -181,10 +181,11 @@ def solve_burgers_si(domain, initial_condition=burgers_initial_condition, dt=Non
 
 def solve_advection(domain, initial_condition=advection_initial_condition, velocity=advection_velocity, dt=None,
                     num_steps=None, hmax=None, Cvel=0.25, Crv=1.0, CFL=0.5, T=1.0, residual_bc=False,
-                    solver="bicgstab", lin_rtol=1e-13, device=0, h=None, return_stats=False):
+                    solver="bicgstab", lin_rtol=1e-13, device=0, h=None, return_stats=False, viscosity="rv"):
     """Linear advection, nodal RV, CN system rebuilt each step (``RV_node_convergence.py``).
 
-    One GFEM step, then ``num_steps - 1`` RV steps, as the reference.
+    One GFEM step, then ``num_steps - 1`` RV steps, as the reference.  ``viscosity="none"``: plain Galerkin
+    Crank-Nicolson in every step (``Code/Linear_advection/linear_advection.py:112-176``).
     """
     ctx = domain if isinstance(domain, Context) else Context.for_domain(domain, device=device)
     u0 = _interpolate(ctx, initial_condition)
@@ -197,7 +198,20 @@ def solve_advection(domain, initial_condition=advection_initial_condition, veloc
     ctx.state_set(uh=u0, u_n=u0, u_old=u0, u_oo=u0, RH=np.zeros(ctx.n), h=h, w=w, t=0.0)
     p = step_params(L.FLUX_ADVECTION, dt, Cvel, Crv, scheme="bdf1", solver=solver, lin_rtol=lin_rtol,
                     bc_kind="constant", bc_value=0.0, residual_bc=residual_bc)
-    stats = ctx.step_advection(p, num_steps, first_gfem=True)
+    if viscosity == "none":
+        stats = None
+        for _ in range(num_steps):     # a "first" (Galerkin) step every time; the state stays on the device
+            st = ctx.step_advection(p, 1, first_gfem=True)
+            if stats is None:
+                stats = st
+            else:
+                for key in ("steps", "krylov_iterations", "kernel_launches", "spmv_launches", "assembly_launches", "device_ms"):
+                    stats[key] += st[key]
+                stats["time"] = st["time"]
+    elif viscosity == "rv":
+        stats = ctx.step_advection(p, num_steps, first_gfem=True)
+    else:
+        raise ValueError("viscosity must be 'rv' or 'none'")
     out = ctx.state_get(("uh", "eps", "RH"))
     uh = NodalFunction(out["uh"], "uh")
     if return_stats:

@@ -419,6 +419,18 @@ def run_advection(x, cells, dt, num_steps, Cvel=0.25, Crv=1.0, u0=None, w=None, 
     return uh, eps, m, h
 
 
+def run_advection_gfem(x, cells, dt, num_steps, u0=None, w=None):
+    """``Code/Linear_advection/linear_advection.py:112-176``: Galerkin Crank-Nicolson, constant system matrix."""
+    x = np.asarray(x, dtype=np.float64)
+    m = Mesh(x, cells)
+    u = advection_initial_condition(x) if u0 is None else np.array(u0, dtype=np.float64)
+    w = advection_velocity(x) if w is None else w
+    A, B = advection_system(m, dt, w)
+    for _ in range(num_steps):
+        u = advection_solve(m, A, B, u)
+    return u, m
+
+
 def run_advection_rk4(x, cells, dt, num_steps, u0=None, w=None):
     """``Code/Linear_advection/GFEM_RK4.py:134-218``: Galerkin linear advection, classical RK4 in time; every
     stage solves ``M_bc k = -int (w . grad u) v`` with homogeneous Dirichlet rows (LU in the reference)."""

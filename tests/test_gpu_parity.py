@@ -328,6 +328,17 @@ def test_burgers_si_steps(smooth_l):
     assert rel(stats["eps"], eps_ref) < 1e-4
 
 
+def test_advection_gfem_steps():
+    """linear_advection.py:112-176: Galerkin CN every step."""
+    x, c = meshes.jittered(30, 30, (-1, -1), (1, 1))
+    dt = S.advection_dt(S.advection_velocity(x), 1 / 15)
+    ref, m = S.run_advection_gfem(x, c, dt, 9)
+    uh, st = GS.solve_advection((x, c), dt=dt, num_steps=9, viscosity="none", return_stats=True)
+    assert st["steps"] == 9 and rel(uh.x.array, ref) < TOL_FIELD
+    rv_run = GS.solve_advection((x, c), dt=dt, num_steps=9)
+    assert rel(rv_run.x.array, ref) > 1e-6      # the RV run is a different scheme
+
+
 def test_advection_rk4_steps():
     """GFEM_RK4.py:134-218, four mass solves per step."""
     x, c = meshes.jittered(30, 30, (-1, -1), (1, 1))
