@@ -205,16 +205,29 @@ def read_mesh(path):
 class XdmfWriter:
     """``io.XDMFFile(comm, path, "w")`` + ``write_mesh`` + ``write_function(f, t)`` of the reference loops."""
 
-    def __init__(self, path, x, cells):
+    def __init__(self, path, x, cells, heavy="binary"):
+        """``heavy="binary"``: raw little-endian sidecar ``<name>.bin``; ``heavy="hdf5"``: ``<name>.h5`` laid out
+        like dolfinx's (``/Mesh/mesh/{topology,geometry}``, ``/Function/<name>/<t with . -> _>``)."""
         self.path = path
-        self.bin_name = os.path.splitext(os.path.basename(path))[0] + ".bin"
-        self._bin = open(os.path.join(os.path.dirname(os.path.abspath(path)), self.bin_name), "wb")
+        folder = os.path.dirname(os.path.abspath(path))
+        stem = os.path.splitext(os.path.basename(path))[0]
         x = np.ascontiguousarray(x, dtype="<f8")
-        cells = np.ascontiguousarray(cells, dtype="<i4")
-        self.nn, self.gdim, self.nc = x.shape[0], x.shape[1], cells.shape[0]
-        self._topo_off = self._append(cells)
-        self._geom_off = self._append(x)
-        self._frames = []   # (name, t, offset, ncomp)
+        self.nn, self.gdim, self.nc = x.shape[0], x.shape[1], np.asarray(cells).shape[0]
+        self._frames = []   # (name, t, offset | dataset path, ncomp)
+        self._h5 = self._bin = None
+        if heavy == "hdf5":
+            self.bin_name = stem + ".h5"
+            self._h5 = H5Writer(os.path.join(folder, self.bin_name))
+            self._h5.write("/Mesh/mesh/topology", np.ascontiguousarray(cells, dtype="<i8"))
+            self._h5.write("/Mesh/mesh/geometry", x)
+            self._h5.flush()
+        elif heavy == "binary":
+            self.bin_name = stem + ".bin"
+            self._bin = open(os.path.join(folder, self.bin_name), "wb")
+            self._topo_off = self._append(np.ascontiguousarray(cells, dtype="<i4"))
+            self._geom_off = self._append(x)
+        else:
+            raise ValueError("heavy must be 'binary' or 'hdf5'")
         self._flush_xml()
 
     def _append(self, a):
@@ -225,35 +238,45 @@ class XdmfWriter:
     def write_function(self, f, t, name=None):
         a = f.x.array if hasattr(f, "x") and hasattr(f.x, "array") else f
         a = np.ascontiguousarray(a, dtype="<f8").reshape(self.nn, -1)
-        self._frames.append((name or getattr(f, "name", "f"), float(t), self._append(a), a.shape[1]))
-        self._bin.flush()
+        name = name or getattr(f, "name", "f")
+        if self._h5:
+            where = f"/Function/{name}/{repr(float(t)).replace('.', '_')}"
+            self._h5.write(where, a)
+            self._h5.flush()
+        else:
+            where = self._append(a)
+            self._bin.flush()
+        self._frames.append((name, float(t), where, a.shape[1]))
         self._flush_xml()
 
+    def _item(self, dims, kind, prec, where):
+        if self._h5:
+            return f'<DataItem Dimensions="{dims}" NumberType="{kind}" Precision="{prec}" Format="HDF">{self.bin_name}:{where}</DataItem>'
+        return (f'<DataItem Dimensions="{dims}" NumberType="{kind}" Precision="{prec}" Format="Binary" Endian="Little" '
+                f'Seek="{where}">{self.bin_name}</DataItem>')
+
     def _flush_xml(self):
-        L = ['<?xml version="1.0"?>', '<Xdmf Version="3.0">', "  <Domain>", '    <Grid Name="mesh" GridType="Uniform">',
-             f'      <Topology TopologyType="Triangle" NumberOfElements="{self.nc}" NodesPerElement="3">',
-             f'        <DataItem Dimensions="{self.nc} 3" NumberType="Int" Precision="4" Format="Binary" Endian="Little" Seek="{self._topo_off}">{self.bin_name}</DataItem>',
-             "      </Topology>", f'      <Geometry GeometryType="{"XY" if self.gdim == 2 else "XYZ"}">',
-             f'        <DataItem Dimensions="{self.nn} {self.gdim}" NumberType="Float" Precision="8" Format="Binary" Endian="Little" Seek="{self._geom_off}">{self.bin_name}</DataItem>',
-             "      </Geometry>", "    </Grid>"]
+        topo = self._item(f"{self.nc} 3", "Int", 8 if self._h5 else 4, "/Mesh/mesh/topology" if self._h5 else self._topo_off)
+        geom = self._item(f"{self.nn} {self.gdim}", "Float", 8, "/Mesh/mesh/geometry" if self._h5 else self._geom_off)
+        gtype = "XY" if self.gdim == 2 else "XYZ"
+        mesh = [f'<Topology TopologyType="Triangle" NumberOfElements="{self.nc}" NodesPerElement="3">', "  " + topo,
+                "</Topology>", f'<Geometry GeometryType="{gtype}">', "  " + geom, "</Geometry>"]
+        L = ['<?xml version="1.0"?>', '<Xdmf Version="3.0">', "  <Domain>", '    <Grid Name="mesh" GridType="Uniform">']
+        L += ["      " + m for m in mesh] + ["    </Grid>"]
         names = []
         for nm, *_ in self._frames:
             if nm not in names:
                 names.append(nm)
         for nm in names:
             L.append(f'    <Grid Name="{nm}" GridType="Collection" CollectionType="Temporal">')
-            for n2, t, off, k in self._frames:
+            for n2, t, where, k in self._frames:
                 if n2 != nm:
                     continue
-                L += [f'      <Grid Name="{nm}" GridType="Uniform">',
-                      f'        <Topology TopologyType="Triangle" NumberOfElements="{self.nc}" NodesPerElement="3">',
-                      f'          <DataItem Dimensions="{self.nc} 3" NumberType="Int" Precision="4" Format="Binary" Endian="Little" Seek="{self._topo_off}">{self.bin_name}</DataItem>',
-                      "        </Topology>", f'        <Geometry GeometryType="{"XY" if self.gdim == 2 else "XYZ"}">',
-                      f'          <DataItem Dimensions="{self.nn} {self.gdim}" NumberType="Float" Precision="8" Format="Binary" Endian="Little" Seek="{self._geom_off}">{self.bin_name}</DataItem>',
-                      "        </Geometry>", f'        <Time Value="{t!r}" />',
+                L.append(f'      <Grid Name="{nm}" GridType="Uniform">')
+                L += ["        " + m for m in mesh]
+                L += [f'        <Time Value="{t!r}" />',
                       f'        <Attribute Name="{nm}" AttributeType="{"Scalar" if k == 1 else "Vector"}" Center="Node">',
-                      f'          <DataItem Dimensions="{self.nn} {k}" NumberType="Float" Precision="8" Format="Binary" Endian="Little" Seek="{off}">{self.bin_name}</DataItem>',
-                      "        </Attribute>", "      </Grid>"]
+                      "          " + self._item(f"{self.nn} {k}", "Float", 8, where), "        </Attribute>", "      </Grid>"]
             L.append("    </Grid>")
         L += ["  </Domain>", "</Xdmf>"]
         tmp = self.path + ".tmp"
@@ -265,9 +288,176 @@ class XdmfWriter:
         if self._bin:
             self._bin.close()
             self._bin = None
+        if self._h5:
+            self._h5.close()
+            self._h5 = None
 
     def __enter__(self):
         return self
 
     def __exit__(self, *exc):
         self.close()
+
+
+# --------------------------------------------------------------------------------------- HDF5 writing side
+class H5Writer:
+    """Writes the same HDF5 subset ``H5File`` reads -- what dolfinx's ``XDMFFile`` produces with the library's
+    default ("earliest") file format: version-0 superblock, old-style groups (local heap + version-1 B-tree of
+    symbol nodes, leaf K = 4, internal K = 16), version-1 object headers, contiguous little-endian datasets.
+
+    Raw data is appended as ``write`` is called; ``flush`` appends a fresh copy of the (small) metadata tree and
+    points the superblock at it, so the file is a complete HDF5 file after every flush and a run can stream
+    snapshots into it.  Message encodings are byte-identical to the ones libhdf5 wrote into the reference's
+    ``Data/*.h5`` (checked in ``tests/test_io.py`` when the reference tree is mounted); the files have not been
+    opened with libhdf5 itself in this image (no h5py / HDF5 tools here)."""
+
+    _SNOD_MAX, _TREE_MAX = 8, 32          # 2 x leaf K, 2 x internal K
+    _F64 = bytes.fromhex("11203f000800000000004000340b0034ff03000000000000")
+    _FILL = bytes.fromhex("0202020100000000")
+
+    def __init__(self, path):
+        self.path = path
+        self._f = open(path, "wb+")
+        self._f.write(b"\0" * 96)
+        self._dsets = {}                    # "/a/b/name" -> (shape, dtype, address, nbytes)
+        self._mtime = 0
+
+    # -- raw data
+    def _alloc(self, blob):
+        f = self._f
+        f.seek(0, 2)
+        pad = (-f.tell()) % 8
+        f.write(b"\0" * pad)
+        addr = f.tell()
+        f.write(blob)
+        return addr
+
+    def write(self, name, array):
+        a = np.asarray(array)
+        if a.dtype.kind == "f":
+            a = np.ascontiguousarray(a, dtype="<f8")
+        elif a.dtype.kind in "iu":
+            a = np.ascontiguousarray(a, dtype="<i8" if a.dtype.itemsize == 8 else "<i4")
+        else:
+            raise H5Error(f"unsupported dtype {a.dtype}")
+        if not name.startswith("/") or name in self._dsets:
+            raise H5Error(f"bad or duplicate dataset path {name!r}")
+        self._dsets[name] = (a.shape, a.dtype, self._alloc(a.tobytes()), a.nbytes)
+
+    # -- metadata
+    @staticmethod
+    def _msg(mtype, body, flags=0):
+        assert len(body) % 8 == 0
+        return struct.pack("<HHB3x", mtype, len(body), flags) + body
+
+    def _dataset_header(self, shape, dtype, addr, nbytes):
+        rank = len(shape)
+        space = struct.pack("<BBB5x", 1, rank, 1) + struct.pack(f"<{2 * rank}Q", *shape, *shape)
+        if dtype.kind == "f":
+            dt = self._F64
+        else:
+            dt = struct.pack("<BBBBIHH4x", 0x10, 0x08, 0, 0, dtype.itemsize, 0, 8 * dtype.itemsize)
+        layout = struct.pack("<BBQQ6x", 3, 1, addr, nbytes)
+        msgs = [self._msg(0x0001, space), self._msg(0x0003, dt, 1), self._msg(0x0005, self._FILL, 1),
+                self._msg(0x0008, layout), self._msg(0x0012, struct.pack("<B3xI", 1, self._mtime))]
+        body = b"".join(msgs)
+        return self._alloc(struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(body)) + body)
+
+    @staticmethod
+    def _balanced(items, cap):
+        n = len(items)
+        k = max(1, -(-n // cap))
+        base, extra = divmod(n, k)
+        out, p = [], 0
+        for i in range(k):
+            m = base + (1 if i < extra else 0)
+            out.append(items[p:p + m])
+            p += m
+        return out
+
+    def _group(self, entries):
+        """entries: name -> (header address, cache type, scratch 16 bytes).  Returns (btree, heap) addresses."""
+        names = sorted(entries)                                   # strcmp order (ASCII names)
+        heap, off = bytearray(8), {}
+        for nm in names:
+            off[nm] = len(heap)
+            raw = nm.encode() + b"\0"
+            heap += raw + b"\0" * ((-len(raw)) % 8)
+        free_at = len(heap)
+        heap += struct.pack("<QQ", 1, 16)                          # one free block: (no next, its own size)
+        data_addr = self._alloc(bytes(heap))
+        heap_addr = self._alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), free_at, data_addr))
+        # symbol nodes
+        level = []                                                # (address, heap offset of the largest name)
+        for chunk in self._balanced(names, self._SNOD_MAX):
+            body = bytearray()
+            for nm in chunk:
+                hdr, ctype, scratch = entries[nm]
+                body += struct.pack("<QQII", off[nm], hdr, ctype, 0) + scratch
+            body += b"\0" * (40 * (self._SNOD_MAX - len(chunk)))
+            level.append((self._alloc(b"SNOD" + struct.pack("<BBH", 1, 0, len(chunk)) + bytes(body)), off[chunk[-1]]))
+        # B-tree levels, bottom up; sibling links need the node addresses first
+        depth = 0
+        while True:
+            groups = self._balanced(level, self._TREE_MAX)
+            size = 24 + 8 * (2 * self._TREE_MAX + 1) + 8 * 2 * self._TREE_MAX
+            addrs = [self._alloc(b"\0" * size) for _ in groups]
+            nxt, left_key = [], 0
+            for i, g in enumerate(groups):
+                node = bytearray(b"TREE" + struct.pack("<BBHQQ", 0, depth, len(g), addrs[i - 1] if i else _UNDEF,
+                                                       addrs[i + 1] if i + 1 < len(groups) else _UNDEF))
+                node += struct.pack("<Q", left_key)
+                for child, kmax in g:
+                    node += struct.pack("<QQ", child, kmax)
+                node += b"\0" * (size - len(node))
+                self._f.seek(addrs[i])
+                self._f.write(node)
+                left_key = g[-1][1]
+                nxt.append((addrs[i], left_key))
+            if len(nxt) == 1:
+                return nxt[0][0], heap_addr
+            level, depth = nxt, depth + 1
+
+    def flush(self):
+        import time
+
+        self._mtime = int(time.time())
+        tree = {}
+        for path, rec in self._dsets.items():
+            parts = path.strip("/").split("/")
+            d = tree
+            for p in parts[:-1]:
+                d = d.setdefault(p, {})
+                if not isinstance(d, dict):
+                    raise H5Error(f"{path}: a dataset is used as a group")
+            d[parts[-1]] = rec
+
+        def emit(node):
+            ent = {}
+            for nm, child in node.items():
+                if isinstance(child, dict):
+                    bt, hp = emit(child)
+                    stab = struct.pack("<QQ", bt, hp)
+                    hdr = self._alloc(struct.pack("<BBHII4x", 1, 0, 1, 1, 24) + self._msg(0x0011, stab))
+                    ent[nm] = (hdr, 1, stab)
+                else:
+                    ent[nm] = (self._dataset_header(*child), 0, b"\0" * 16)
+            return self._group(ent)
+
+        bt, hp = emit(tree)
+        stab = struct.pack("<QQ", bt, hp)
+        root = self._alloc(struct.pack("<BBHII4x", 1, 0, 1, 1, 24) + self._msg(0x0011, stab))
+        self._f.seek(0, 2)
+        eof = self._f.tell()
+        sb = (b"\x89HDF\r\n\x1a\n" + bytes([0, 0, 0, 0, 0, 8, 8, 0]) + struct.pack("<HHI", 4, 16, 0) +
+              struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF) + struct.pack("<QQII", 0, root, 1, 0) + stab)
+        assert len(sb) == 96
+        self._f.seek(0)
+        self._f.write(sb)
+        self._f.flush()
+
+    def close(self):
+        if self._f:
+            self.flush()
+            self._f.close()
+            self._f = None
