@@ -23,6 +23,7 @@ SOLVER_PCG, SOLVER_BICGSTAB, SOLVER_GMRES, SOLVER_CHEBYSHEV = 0, 1, 2, 3
 BC_CONSTANT, BC_BURGERS_EXACT, BC_USER = 0, 1, 2
 ORDER_HILBERT, ORDER_NATURAL = 0, 1
 KERNEL_SPMV, KERNEL_ASM_RESIDUAL, KERNEL_ASM_JACOBIAN, KERNEL_RV_EPSILON, KERNEL_ASM_RV_RHS = 0, 1, 2, 3, 4
+KERNEL_COMM_ALLREDUCE, KERNEL_COMM_HALO, KERNEL_SPMV_SYSTEM, KERNEL_CHEB_ITER = 6, 7, 8, 9
 
 FLUX_BY_NAME = {"advection": FLUX_ADVECTION, "burgers": FLUX_BURGERS, "kpp": FLUX_KPP}
 SOLVER_BY_NAME = {"pcg": SOLVER_PCG, "bicgstab": SOLVER_BICGSTAB, "gmres": SOLVER_GMRES, "chebyshev": SOLVER_CHEBYSHEV}
@@ -123,7 +124,8 @@ SIGNATURES = {
 
 HM_ARRAYS = {"n2u": 0, "cells": 1, "rowptr": 2, "colidx": 3, "v2c_ptr": 4, "v2c_code": 5, "tile_node": 6,
              "tile_cellptr": 7, "tile_cells": 8, "is_bnd": 9, "bnd_user": 10, "peer_rank": 11, "send_ptr": 12,
-             "send_idx": 13, "recv_off": 14, "recv_cnt": 15, "last_cell": 16}
+             "send_idx": 13, "recv_off": 14, "recv_cnt": 15, "last_cell": 16, "lc16": 17, "tile_extptr": 18,
+             "tile_ext": 19, "tile_order": 20}
 
 
 def host_analyse(x, cells, order=ORDER_HILBERT, rank=0, world=1):
@@ -143,7 +145,7 @@ def host_analyse(x, cells, order=ORDER_HILBERT, rank=0, world=1):
     try:
         for name, what in HM_ARRAYS.items():
             n = lib.cfem_host_size(h, what)
-            dt = np.uint8 if name == "is_bnd" else (np.uint32 if name == "v2c_code" else np.int32)
+            dt = {"is_bnd": np.uint8, "v2c_code": np.uint32, "lc16": np.uint16}.get(name, np.int32)
             a = np.empty(n, dtype=dt)
             check(lib.cfem_host_copy(h, what, ptr(a)))
             out[name] = a

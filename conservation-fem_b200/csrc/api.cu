@@ -2,6 +2,7 @@
 // argument staging with the internal<->caller permutation, the single-operator
 // entry points, and the time loops.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -254,10 +255,52 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   dm.ntiles = (int)hm.tile_node.size() - 1;
   dm.xy = (const double2*)upload(c, hm.xy);
   dm.cells = upload(c, hm.cells);
-  { std::vector<int32_t> rp(hm.rowptr), ci(hm.colidx);  // padded copies for the aligned bulk-copy windows
+  { // hot block: MASS_BC values | rowptr | lc16 | extptr | ext | SYSTEM values | colidx (one allocation: see cfem_ctx::hot_base)
+    std::vector<int32_t> rp(hm.rowptr), ci(hm.colidx);  // padded copies for the aligned bulk-copy windows
     rp.resize(rp.size() + 8, rp.back()); ci.resize(ci.size() + 8, 0);
-    dm.rowptr = upload(c, rp);
-    dm.colidx = upload(c, ci); }
+    std::vector<uint16_t> lc(hm.lc16);
+    lc.resize(lc.size() + 16, 0);
+    auto up256 = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t vbytes = up256((size_t)(hm.nnz + 8) * sizeof(double));
+    size_t* off = c->hot_off;
+    off[0] = 0;
+    off[1] = vbytes;
+    off[2] = off[1] + up256(rp.size() * sizeof(int32_t));
+    off[3] = off[2] + up256(lc.size() * sizeof(uint16_t));
+    off[4] = off[3] + up256(hm.tile_extptr.size() * sizeof(int32_t));
+    off[5] = off[4] + up256((hm.tile_ext.size() + 8) * sizeof(int32_t));
+    off[6] = off[5] + vbytes;
+    off[7] = off[6] + up256(ci.size() * sizeof(int32_t));
+    c->hot_base = (char*)dalloc<char>(c, (int64_t)off[7]);
+    auto put = [&](size_t o, const void* src, size_t bytes) {
+      if (bytes) CUDA_OK(cudaMemcpy(c->hot_base + o, src, bytes, cudaMemcpyHostToDevice));
+    };
+    put(off[1], rp.data(), rp.size() * sizeof(int32_t));
+    put(off[2], lc.data(), lc.size() * sizeof(uint16_t));
+    put(off[3], hm.tile_extptr.data(), hm.tile_extptr.size() * sizeof(int32_t));
+    put(off[4], hm.tile_ext.data(), hm.tile_ext.size() * sizeof(int32_t));
+    put(off[6], ci.data(), ci.size() * sizeof(int32_t));
+    dm.rowptr = (const int32_t*)(c->hot_base + off[1]);
+    dm.lc16 = (const uint16_t*)(c->hot_base + off[2]);
+    dm.tile_extptr = (const int32_t*)(c->hot_base + off[3]);
+    dm.tile_ext = (const int32_t*)(c->hot_base + off[4]);
+    dm.colidx = (const int32_t*)(c->hot_base + off[6]);
+    dm.ext_cap = (hm.max_tile_ext + 31) / 32 * 32;
+    std::vector<uint16_t>().swap(hm.lc16);
+    std::vector<int32_t>().swap(hm.tile_ext);
+    // persisting-L2 set-aside (device wide): as much as the device allows unless CFEM_L2_SETASIDE_MB says otherwise
+    const char* l2off = getenv("CFEM_L2PERSIST");
+    if (!(l2off && std::string(l2off) == "0") && prop.persistingL2CacheMaxSize > 0) {
+      size_t want = (size_t)prop.persistingL2CacheMaxSize;
+      if (const char* mb = getenv("CFEM_L2_SETASIDE_MB")) want = std::min(want, (size_t)atol(mb) << 20);
+      if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        c->l2_setaside = want;
+        c->l2_max_window = (size_t)prop.accessPolicyMaxWindowSize;
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
   dm.v2c_ptr = upload(c, hm.v2c_ptr);
   dm.v2c_code = upload(c, hm.v2c_code);
   dm.tile_node = upload(c, hm.tile_node);
@@ -283,7 +326,10 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   std::vector<int32_t>().swap(hm.tile_cells);
   if (world > 1) CUDA_OK(cudaMallocHost((void**)&c->h_stage, 4 * nn * sizeof(double)));
   for (int k = 0; k < 4; ++k) {
-    c->mat[k].vals = dalloc<double>(c, hm.nnz + 8);  // +8: 16-byte aligned bulk-copy windows may overrun the last tile
+    // +8: 16-byte aligned bulk-copy windows may overrun the last tile
+    if (k == CFEM_MAT_MASS_BC) c->mat[k].vals = (double*)(c->hot_base + c->hot_off[0]);
+    else if (k == CFEM_MAT_SYSTEM) c->mat[k].vals = (double*)(c->hot_base + c->hot_off[5]);
+    else c->mat[k].vals = dalloc<double>(c, hm.nnz + 8);
     c->mat[k].dinv = dalloc<double>(c, nn);
   }
   double** state[] = {&c->uh, &c->u_n, &c->u_old, &c->u_oo, &c->RH, &c->eps, &c->h, &c->g, &c->fluxn};
@@ -994,7 +1040,12 @@ int cfem_time_kernel(cfem_ctx* c, int kernel, int flux, int reps, double* ms_per
   Matrix& J = c->mat[CFEM_MAT_SYSTEM];
   auto body = [&]() {
     switch (kernel) {
-      case CFEM_KERNEL_SPMV: launch_spmv(c, M, c->u_n, c->wk[9]); bytes = 12.0 * nnz + 4.0 * (nn + 1) + 16.0 * nn; break;
+      case CFEM_KERNEL_SPMV: l2_prefer(c, M); launch_spmv(c, M, c->u_n, c->wk[9]); bytes = 12.0 * nnz + 4.0 * (nn + 1) + 16.0 * nn; break;
+      case CFEM_KERNEL_SPMV_SYSTEM:
+        if (!J.valid) CFEM_THROW(-1, "time_kernel: no system matrix assembled yet");
+        l2_prefer(c, J);
+        launch_spmv_dots2(c, J, c->u_n, c->wk[9], c->wk[8], c->partials + 5 * kMaxPartials, c->partials + 6 * kMaxPartials);
+        bytes = 12.0 * nnz + 4.0 * (nn + 1) + 24.0 * nn; break;
       case CFEM_KERNEL_ASM_RESIDUAL:
         launch_cn_residual(c, flux, dt, c->uh, c->u_n, c->eps, c->g, c->fluxn, c->wk[8], c->partials + 7 * kMaxPartials);
         bytes = meta + 8.0 * 5 * nn + 8.0 * nn; break;   // uh,u_n,eps,g,fluxn in; F out
@@ -1057,6 +1108,10 @@ static auto host_array(const cfem_host_mesh* h, int what, F&& f) {
     case CFEM_HM_RECV_OFF: return f(m.recv_off.data(), m.recv_off.size(), 4);
     case CFEM_HM_RECV_CNT: return f(m.recv_cnt.data(), m.recv_cnt.size(), 4);
     case CFEM_HM_LAST_CELL: return f(m.last_cell.data(), m.last_cell.size(), 4);
+    case CFEM_HM_LC16: return f(m.lc16.data(), m.lc16.size(), 2);
+    case CFEM_HM_TILE_EXTPTR: return f(m.tile_extptr.data(), m.tile_extptr.size(), 4);
+    case CFEM_HM_TILE_EXT: return f(m.tile_ext.data(), m.tile_ext.size(), 4);
+    case CFEM_HM_TILE_ORDER: return f(m.tile_order.data(), m.tile_order.size(), 4);
     default: return f(nullptr, (size_t)0, 0);
   }
 }

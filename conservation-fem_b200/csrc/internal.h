@@ -56,6 +56,14 @@ struct HostMesh {
   std::vector<int32_t> tile_node;         // ntiles+1
   std::vector<int32_t> tile_cellptr;      // ntiles+1
   std::vector<int32_t> tile_cells;        // concatenated cell lists
+  // T16 tile format of the SpMV-type kernels: a tile's CSR columns as 16-bit tile-local indices.  Index < kTileNodes:
+  // the tile's own row (n0 + index); otherwise kTileNodes + position in the tile's EXTERNAL column list (distinct
+  // columns outside the tile, ascending -> ghost columns last).  A kernel stages x for own rows (coalesced) and
+  // externals (one gather each) in shared memory once per tile instead of gathering x per CSR entry.
+  std::vector<uint16_t> lc16;             // nnz
+  std::vector<int32_t> tile_extptr;       // ntiles+1
+  std::vector<int32_t> tile_ext;          // concatenated external column lists (local node ids)
+  int max_tile_ext = 0;
   std::vector<int32_t> tile_order;        // tiles whose rows touch no ghost column first, the others last
   int n_interior_tiles = 0;
   std::vector<uint8_t> is_bnd;            // nn
@@ -84,6 +92,10 @@ struct DevMesh {
   const int32_t* tile_node;
   const int32_t* tile_cellptr;
   const int32_t* tile_cells;
+  const uint16_t* lc16;        // T16 format, see HostMesh
+  const int32_t* tile_extptr;
+  const int32_t* tile_ext;
+  int ext_cap;                 // max external columns of any tile, rounded up to a multiple of 32
   const int32_t* tile_order;   // interior tiles first (identity on one GPU)
   int n_interior;              // number of tiles that need no ghost value
   const uint8_t* is_bc;    // current Dirichlet flags
@@ -176,4 +188,13 @@ struct cfem_ctx {
   int pcg_predict = 28, krylov_predict = 8;
   double* dx_guess = nullptr;   // first Newton update of the previous step (initial guess of the next Krylov solve)
   bool dx_guess_valid = false;
+  // ---- L2 residency of the matrix a solve streams repeatedly (linalg.cu: l2_prefer).  MASS_BC values, the T16
+  // pattern tables and SYSTEM values are carved from ONE allocation in that order, so either matrix together with
+  // the shared pattern is one contiguous access-policy window.
+  char* hot_base = nullptr;
+  size_t hot_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // MASS_BC vals | rowptr | lc16 | extptr | ext | SYSTEM vals | colidx | end
+  size_t l2_setaside = 0;                // bytes of L2 set aside for persisting lines (0: feature off)
+  size_t l2_max_window = 0;
+  int t16_grid = 0;                      // grid of the T16 tile kernels (occupancy x SMs, <= tiles), 0 = not sized yet
+  int l2_window = 0;                     // matrix id whose window is currently attached to the stream, -1 none
 };

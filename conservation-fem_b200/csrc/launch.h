@@ -36,6 +36,8 @@ void smooth_plan_free(cfem_ctx* c);
 
 // ---- linear algebra (linalg.cu) ------------------------------------------------
 void launch_spmv(cfem_ctx* c, const Matrix& A, const double* x, double* y);
+// y = A x with the two fused dot products (y, d0) and (y, y) of a BiCGStab iteration (measurement hook)
+void launch_spmv_dots2(cfem_ctx* c, const Matrix& A, const double* x, double* y, const double* d0, double* p0, double* p1);
 void launch_gather(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n);      // dst[i] = src[idx[i]]
 void launch_scatter(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n);     // dst[idx[i]] = src[i]
 void launch_gather2(cfem_ctx* c, const double2* src, const int32_t* idx, double2* dst, int64_t n);
@@ -60,6 +62,9 @@ SolveResult bicgstab_generic(cfem_ctx* c, int64_t n, int halo_width, const doubl
 SolveResult gmres(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol,
                   double atol, int max_it, int* predict);
 double norm2(cfem_ctx* c, const double* v, int64_t n);  // synchronous
+// Attach the access-policy window of matrix A (values + pattern -> persisting L2 lines) to the context stream;
+// no-op for matrices outside the hot block or when CFEM_L2PERSIST=0.
+void l2_prefer(cfem_ctx* c, const Matrix& A);
 
 // ---- multi-GPU (comm.cu); every call is a no-op when world == 1 --------------------
 void comm_unique_id(void* out128);

@@ -9,6 +9,7 @@
 // results are bitwise reproducible.  A device-side `done` flag turns the
 // remaining launches of a chunk into no-ops; the host polls it every few
 // iterations (after a predicted iteration count) instead of every iteration.
+#include <algorithm>
 #include <cstdlib>
 #include <string>
 
@@ -30,6 +31,57 @@ static inline int vec_grid(const cfem_ctx* c, int64_t n) {
 enum { P_PQ = 0, P_RZ0 = 1, P_RZ1 = 2, P_RR = 3, P_BB = 4, P_A = 5, P_B = 6, P_C = 7 };
 // device scalars
 enum { S_SUM = 0, S_MIN = 1, S_MAX = 2, S_BB = 3, S_ALPHA = 4, S_OMEGA = 5, S_RHO = 6, S_RELRES = 7, S_RR = 8 };
+
+// SpMV-type kernel family (A/B switch CFEM_SPMV, default t16):
+//   t16     staged tile kernels over the 16-bit tile-local column format (k_tile_t16)
+//   stream  CSR-stream tile kernels, one x gather per entry (k_spmv_stream / k_cheb_stream; round-1 default)
+//   tma     TMA-staged variant of the stream kernels (measured slower)
+//   subwarp sub-warp per row
+static int g_spmv_mode = -1;  // 0 = tile kernels, 1 = sub-warp per row
+static int g_spmv_tma = 0;
+static int g_spmv_t16 = 1;
+static inline int spmv_mode() {
+  if (g_spmv_mode < 0) {
+    const char* e = getenv("CFEM_SPMV");
+    const std::string m = e ? e : "";
+    g_spmv_mode = m == "subwarp" ? 1 : 0;
+    g_spmv_tma = m == "tma" ? 1 : 0;
+    g_spmv_t16 = (m == "stream" || m == "tma" || m == "subwarp") ? 0 : 1;
+  }
+  return g_spmv_mode;
+}
+
+// ---------------------------------------------------------------- L2 residency of the solve's matrix
+// A Krylov / Chebyshev solve streams the same matrix 20-60 times; at ~1 M rows its values + pattern (88 MB) fit
+// the persisting part of the 126 MB L2.  The window covers [values | rowptr | colidx] (MASS_BC) or
+// [rowptr | colidx | values] (SYSTEM) of the hot block; when it is larger than the set-aside, hitRatio keeps a
+// fixed random subset of its lines persisting instead of letting them thrash.  Vector traffic misses as
+// "streaming" lines, which are the first to be evicted.
+void l2_prefer(cfem_ctx* c, const Matrix& A) {
+  if (!c->l2_setaside) return;
+  int which = -1;
+  if (A.vals == c->mat[CFEM_MAT_MASS_BC].vals) which = CFEM_MAT_MASS_BC;
+  else if (A.vals == c->mat[CFEM_MAT_SYSTEM].vals) which = CFEM_MAT_SYSTEM;
+  if (which == c->l2_window) return;
+  cudaStreamAttrValue attr{};
+  if (which >= 0) {
+    // the legacy CSR-stream kernels (CFEM_SPMV=stream) read colidx, which lies behind the SYSTEM values
+    const size_t lo = which == CFEM_MAT_MASS_BC ? c->hot_off[0] : c->hot_off[1];
+    const size_t hi = which == CFEM_MAT_MASS_BC ? c->hot_off[5] : ((spmv_mode(), g_spmv_t16) ? c->hot_off[6] : c->hot_off[7]);
+    size_t bytes = hi - lo;
+    if (c->l2_max_window && bytes > c->l2_max_window) bytes = c->l2_max_window;
+    attr.accessPolicyWindow.base_ptr = c->hot_base + lo;
+    attr.accessPolicyWindow.num_bytes = bytes;
+    const double ratio = (double)c->l2_setaside / (double)bytes;
+    attr.accessPolicyWindow.hitRatio = ratio < 1.0 ? (float)ratio : 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  } else {
+    attr.accessPolicyWindow.num_bytes = 0;  // detach
+  }
+  CUDA_OK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  c->l2_window = which;
+}
 
 // ---------------------------------------------------------------- basic vector kernels
 __global__ void k_gather(const double* __restrict__ src, const int32_t* __restrict__ idx, double* __restrict__ dst, int64_t n) {
@@ -404,19 +456,193 @@ static void launch_tile_spmv(cfem_ctx* c, const GhostSrc& gsrc, const Matrix& A,
   }
 }
 
-static int g_spmv_mode = -1;  // 0 = tile kernels (default), 1 = sub-warp per row (CFEM_SPMV=subwarp)
-static int g_spmv_tma = 0;    // tile kernels: CFEM_SPMV=tma selects the TMA-staged variant (measured slower)
-static inline int spmv_mode() {
-  if (g_spmv_mode < 0) {
-    const char* e = getenv("CFEM_SPMV");
-    g_spmv_mode = (e && std::string(e) == "subwarp") ? 1 : 0;
-    g_spmv_tma = (e && std::string(e) == "tma") ? 1 : 0;
+// ---------------------------------------------------------------- T16 staged tile kernels (default)
+// Same row arithmetic and summation order as k_spmv_stream / k_cheb_stream, but x is staged ONCE per tile:
+// own rows with one coalesced load, the tile's external columns (~70-130 of them for a 256-row Hilbert tile) with
+// one gather each, ghosts straight from the mailbox.  The CSR stream then is values (8 B) + 16-bit tile-local
+// column (2 B) per entry and every x lookup hits shared memory.  The round-1 kernels gathered x per entry:
+// ~7.3 M 32-byte sectors per launch at 1 M rows, which kept the L2->SM fabric near its ~6300 B/clk cap and is the
+// reason an L2-resident matrix alone would not have helped.  Per launch at 1 M rows: L2->SM traffic ~300 MB -> ~150 MB.
+#ifndef CFEM_T16_MINB
+#define CFEM_T16_MINB 6   // resident CTAs per SM the register budget is held to (<= 42 registers)
+#endif
+struct EpPre { double a, b, c; };
+
+template <int NDOT>
+struct Ep16Spmv {  // y = A x with NDOT fused dot products
+  static constexpr int NACC = NDOT;
+  double* y;
+  const double *d0, *d1;
+  double *p0, *p1;
+  __device__ __forceinline__ EpPre pre(int row) const {
+    EpPre q{0.0, 0.0, 0.0};
+    if (NDOT >= 1 && d0 != y) q.a = d0[row];
+    if (NDOT >= 2 && d1 != y) q.b = d1[row];
+    return q;
   }
-  return g_spmv_mode;
+  __device__ __forceinline__ void row(int row, double s, double, const EpPre& q, double& a0, double& a1) const {
+    y[row] = s;
+    if (NDOT >= 1) a0 += s * (d0 == y ? s : q.a);
+    if (NDOT >= 2) a1 += s * (d1 == y ? s : q.b);
+  }
+};
+
+template <bool FIRST>
+struct Ep16Cheb {  // one Chebyshev iteration of the mass solve: r = b - M x, z = D^-1 r, d = c1 d + c2 z, x+ = x + d
+  static constexpr int NACC = FIRST ? 2 : 1;
+  const double *dinv, *b;
+  double *xn, *d;
+  double c1, c2;
+  double *p0, *p1;  // ||r||^2 , ||b||^2 partials
+  __device__ __forceinline__ EpPre pre(int row) const { return EpPre{b[row], dinv[row], FIRST ? 0.0 : d[row]}; }
+  __device__ __forceinline__ void row(int row, double s, double xown, const EpPre& q, double& a0, double& a1) const {
+    const double r = q.a - s, z = q.b * r;
+    const double dk = FIRST ? c2 * z : c1 * q.c + c2 * z;
+    d[row] = dk;
+    xn[row] = xown + dk;
+    a0 += r * r;
+    if (FIRST) a1 += q.a * q.a;
+  }
+};
+
+template <class EP, bool GHOST>
+__global__ void __launch_bounds__(kTileNodes, CFEM_T16_MINB)
+k_tile_t16(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ tile_order, const int n_interior,
+           const int ntiles, const int32_t* __restrict__ tile_node, const int32_t* __restrict__ rowptr,
+           const uint16_t* __restrict__ lc16, const int32_t* __restrict__ extptr, const int32_t* __restrict__ ext,
+           const double* __restrict__ vals, const double* __restrict__ x, const EP ep,
+           const int32_t* __restrict__ status) {
+  int bid = blockIdx.x, nblk = gridDim.x;
+  if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
+    if (bid == 0) { pdl_wait(); pdl_launch(); push_cta(gsrc.pushdev, x, gsrc.seq, status && status[0]); return; }
+    --bid; --nblk;
+  }
+  extern __shared__ double t16_smem[];
+  double* const prod = t16_smem;               // [kTileNnzCap]
+  double* const xs = t16_smem + kTileNnzCap;   // [kTileNodes + ext_cap]
+  __shared__ int32_t rp[kTileNodes + 1];
+  __shared__ double red[9];
+  const int tid = threadIdx.x;
+  double acc0 = 0.0, acc1 = 0.0;
+  bool waited = false, synced = false;
+  const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;  // mbox_shifted[col] == mailbox[col - no]
+  if (bid >= ntiles) { pdl_wait(); pdl_launch(); }
+  for (int t = bid; t < ntiles; t += nblk) {
+    const int tile = GHOST ? tile_order[t] : t;
+    const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
+    const int e0 = extptr[tile], ne = extptr[tile + 1] - e0;
+    const int start = rowptr[n0], cnt = rowptr[n0 + nrows] - start;
+    for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i] - start;
+    const double* __restrict__ v = vals + start;
+    const uint16_t* __restrict__ lc = lc16 + start;
+    // mesh tables only up to here (nothing a predecessor kernel writes), so under a programmatic launch these
+    // requests overlap the previous kernel's drain; the matrix values may come straight from an assembly kernel
+    const int ecol = tid < ne ? ext[e0 + tid] : 0;
+    int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+    if (tid < cnt) l0 = lc[tid];
+    if (tid + kTileNodes < cnt) l1 = lc[tid + kTileNodes];
+    if (tid + 2 * kTileNodes < cnt) l2 = lc[tid + 2 * kTileNodes];
+    if (tid + 3 * kTileNodes < cnt) l3 = lc[tid + 3 * kTileNodes];
+    if (!synced) {
+      pdl_wait();
+      pdl_launch();
+      synced = true;
+      if (status && status[0]) return;
+    }
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    if (tid < cnt) v0 = v[tid];
+    if (tid + kTileNodes < cnt) v1 = v[tid + kTileNodes];
+    if (tid + 2 * kTileNodes < cnt) v2 = v[tid + 2 * kTileNodes];
+    if (tid + 3 * kTileNodes < cnt) v3 = v[tid + 3 * kTileNodes];
+    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
+    // ---- stage x: own rows, then the external columns
+    double xown = 0.0;
+    if (tid < nrows) { xown = x[n0 + tid]; xs[tid] = xown; }
+    if (tid < ne) xs[kTileNodes + tid] = XG(x, ecol);
+    for (int e = tid + kTileNodes; e < ne; e += kTileNodes) { const int cc = ext[e0 + e]; xs[kTileNodes + e] = XG(x, cc); }
+    EpPre q{0.0, 0.0, 0.0};
+    if (tid < nrows) q = ep.pre(n0 + tid);   // epilogue operands requested before the barrier
+    __syncthreads();
+    // ---- products
+    {
+      const int p = tid;
+      if (p < cnt) prod[p] = v0 * xs[l0];
+      if (p + kTileNodes < cnt) prod[p + kTileNodes] = v1 * xs[l1];
+      if (p + 2 * kTileNodes < cnt) prod[p + 2 * kTileNodes] = v2 * xs[l2];
+      if (p + 3 * kTileNodes < cnt) prod[p + 3 * kTileNodes] = v3 * xs[l3];
+    }
+    for (int p = tid + 4 * kTileNodes; p < cnt; p += kTileNodes) prod[p] = v[p] * xs[lc[p]];
+    __syncthreads();
+    if (tid < nrows) {
+      const int a = rp[tid], b = rp[tid + 1];
+      double s = 0.0;
+      for (int k = a; k < b; ++k) s += prod[k];
+      ep.row(n0 + tid, s, xown, q, acc0, acc1);
+    }
+    __syncthreads();
+  }
+  if (EP::NACC >= 1) {
+    acc0 = block_sum(acc0, red);
+    if (tid == 0) ep.p0[bid] = acc0;
+  }
+  if (EP::NACC >= 2) {
+    acc1 = block_sum(acc1, red);
+    if (tid == 0) ep.p1[bid] = acc1;
+  }
 }
 
-static inline int spmv_grid(const cfem_ctx* c) {
+static size_t t16_smem_bytes(const cfem_ctx* c) { return sizeof(double) * ((size_t)kTileNnzCap + kTileNodes + c->dm.ext_cap); }
+
+template <class EP, bool GHOST>
+static int t16_prepare_one(cfem_ctx* c) {
+  const size_t smem = t16_smem_bytes(c);
+  CUDA_OK(cudaFuncSetAttribute(k_tile_t16<EP, GHOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile_t16<EP, GHOST>, kTileNodes, smem));
+  if (occ < 1) CFEM_THROW(-2, "T16 tile kernel does not fit on an SM (too many external columns per tile)");
+  return occ;
+}
+
+// once per context: opt the instantiations in to the dynamic shared memory this mesh needs and size the grid by
+// the smallest occupancy among them (kept in the context, not in a function static: two contexts may differ)
+static int t16_grid(cfem_ctx* c) {
+  if (c->t16_grid == 0) {
+    int occ = 8;
+    occ = std::min(occ, t16_prepare_one<Ep16Spmv<0>, false>(c));
+    occ = std::min(occ, t16_prepare_one<Ep16Spmv<1>, false>(c));
+    occ = std::min(occ, t16_prepare_one<Ep16Spmv<2>, false>(c));
+    occ = std::min(occ, t16_prepare_one<Ep16Cheb<true>, false>(c));
+    occ = std::min(occ, t16_prepare_one<Ep16Cheb<false>, false>(c));
+    if (c->world > 1 || getenv("CFEM_FORCE_GHOST")) {
+      occ = std::min(occ, t16_prepare_one<Ep16Spmv<0>, true>(c));
+      occ = std::min(occ, t16_prepare_one<Ep16Spmv<1>, true>(c));
+      occ = std::min(occ, t16_prepare_one<Ep16Spmv<2>, true>(c));
+      occ = std::min(occ, t16_prepare_one<Ep16Cheb<true>, true>(c));
+      occ = std::min(occ, t16_prepare_one<Ep16Cheb<false>, true>(c));
+    }
+    const int64_t cap = (int64_t)c->sm_count * occ;
+    c->t16_grid = (int)(c->dm.ntiles < cap ? c->dm.ntiles : cap);
+  }
+  return c->t16_grid;
+}
+
+template <class EP>
+static void launch_t16(cfem_ctx* c, const GhostSrc& gsrc, const Matrix& A, const double* x, const EP& ep, bool gated) {
+  const int grid = t16_grid(c);
+  const size_t smem = t16_smem_bytes(c);
+  const int32_t* st = gated ? c->status : nullptr;
+  const DevMesh& m = c->dm;
+  if (gsrc.mbox)
+    launch_pdl(k_tile_t16<EP, true>, grid + (gsrc.pushdev ? 1 : 0), kTileNodes, smem, c->stream, gsrc, m.no, m.tile_order,
+               m.n_interior, m.ntiles, m.tile_node, m.rowptr, m.lc16, m.tile_extptr, m.tile_ext, A.vals, x, ep, st);
+  else
+    launch_pdl(k_tile_t16<EP, false>, grid, kTileNodes, smem, c->stream, gsrc, m.no, m.tile_order, m.n_interior, m.ntiles,
+               m.tile_node, m.rowptr, m.lc16, m.tile_extptr, m.tile_ext, A.vals, x, ep, st);
+}
+
+static inline int spmv_grid(cfem_ctx* c) {
   const int64_t cap = (int64_t)c->sm_count * 8;
+  if (spmv_mode() == 0 && g_spmv_t16) return t16_grid(c);
   if (spmv_mode() == 0 && g_spmv_tma) return tma_grid(c);
   if (spmv_mode() == 0) return (int)(c->dm.ntiles < cap ? c->dm.ntiles : cap);
   const int64_t rows_per_block = (kBlock / 32) * 4;
@@ -431,7 +657,9 @@ static void spmv_dots(cfem_ctx* c, const Matrix& A, const double* x, double* y, 
   if (spmv_mode() == 0) gsrc = halo_push(c, const_cast<double*>(x), gated, !g_spmv_tma);  // producer half; the kernel waits in its boundary CTAs
   else halo_exchange(c, const_cast<double*>(x));
   ProfScope ps(c, PROF_SPMV);
-  if (spmv_mode() == 0 && g_spmv_tma)
+  if (spmv_mode() == 0 && g_spmv_t16)
+    launch_t16(c, gsrc, A, x, Ep16Spmv<NDOT>{y, d0, d1, p0, p1}, gated);
+  else if (spmv_mode() == 0 && g_spmv_tma)
     launch_tile_spmv(c, gsrc, A, x, EpSpmv<NDOT>{y, d0, d1, p0, p1}, gated);
   else if (spmv_mode() == 0 && gsrc.mbox)
     launch_pdl(k_spmv_stream<NDOT, true>, spmv_grid(c) + (gsrc.pushdev ? 1 : 0), kTileNodes, 0, c->stream, gsrc, c->dm.no,
@@ -455,6 +683,10 @@ static void spmv_dots(cfem_ctx* c, const Matrix& A, const double* x, double* y, 
 
 void launch_spmv(cfem_ctx* c, const Matrix& A, const double* x, double* y) {
   spmv_dots<0>(c, A, x, y, nullptr, nullptr, nullptr, nullptr, false);
+}
+
+void launch_spmv_dots2(cfem_ctx* c, const Matrix& A, const double* x, double* y, const double* d0, double* p0, double* p1) {
+  spmv_dots<2>(c, A, x, y, d0, y, p0, p1, false);
 }
 
 // ---------------------------------------------------------------- Chebyshev (mass matrix)
@@ -545,6 +777,7 @@ k_relres(const double* __restrict__ part, int npart_rr, int npart_bb, double* __
 SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, int max_it,
                            int* predict) {
   const int64_t n = c->dm.nn;  // copies move ghosts too
+  l2_prefer(c, A);
   int np_bb = 0;
   double *xa = x, *xb = c->wk[0], *d = c->wk[1];
   double* part = c->partials;
@@ -569,7 +802,13 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
   launch_pdl(k_cheb_stream<FIRST, GHOST>, gs + (GHOST && gsrc.pushdev ? 1 : 0), kTileNodes, 0, c->stream, gsrc, c->dm.no, \
              c->dm.tile_order, c->dm.n_interior, c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, A.dinv, \
              b, xa, xb, d, C1, C2, part + P_RR * kMaxPartials, PBB)
-      if (g_spmv_tma && it == 0) {
+      if (g_spmv_t16 && it == 0) {
+        launch_t16(c, gsrc, A, xa, Ep16Cheb<true>{A.dinv, b, xb, d, 0.0, 1.0 / theta, part + P_RR * kMaxPartials, part + P_BB * kMaxPartials}, false);
+      } else if (g_spmv_t16) {
+        const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+        launch_t16(c, gsrc, A, xa, Ep16Cheb<false>{A.dinv, b, xb, d, rho_new * rho, 2.0 * rho_new / delta, part + P_RR * kMaxPartials, nullptr}, false);
+        rho = rho_new;
+      } else if (g_spmv_tma && it == 0) {
         launch_tile_spmv(c, gsrc, A, xa, EpCheb<true>{A.dinv, b, xa, xb, d, 0.0, 1.0 / theta, part + P_RR * kMaxPartials, part + P_BB * kMaxPartials}, false);
       } else if (g_spmv_tma) {
         const double rho_new = 1.0 / (2.0 * sigma1 - rho);
@@ -722,6 +961,7 @@ SolveResult pcg(cfem_ctx* c, const Matrix& A, const double* b, double* x, double
                 int max_it, int* predict) {
   const int64_t n = c->dm.no;
   const bool dist = c->world > 1;
+  l2_prefer(c, A);
   double *r = c->wk[0], *z = c->wk[1], *p = c->wk[2], *q = c->wk[3];
   double* part = c->partials;
   const int gv = vec_grid(c, n), gs = spmv_grid(c);
@@ -898,6 +1138,7 @@ SolveResult bicgstab_generic(cfem_ctx* c, int64_t n, int halo_width, const doubl
 
 SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
                      int max_it, int* predict) {
+  l2_prefer(c, A);
   LinApply op = [&](const double* xin, double* yout, int ndot, const double* d0, const double* d1, double* p0,
                     double* p1, bool gated) {
     if (ndot == 0) spmv_dots<0>(c, A, xin, yout, nullptr, nullptr, nullptr, nullptr, gated);
@@ -1079,6 +1320,7 @@ k_gm_xupdate(int64_t n, int64_t stride, const double* __restrict__ V, const doub
 SolveResult gmres(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol, int max_it,
                   int* predict) {
   const int64_t n = c->dm.no, nl = c->dm.nn;
+  l2_prefer(c, A);
   if (!c->gmres_V) {
     void* p = nullptr;
     CUDA_OK(cudaMalloc(&p, (size_t)(kGmresM + 1) * nl * sizeof(double)));

@@ -409,6 +409,39 @@ static void build_tiles(HostMesh& hm, const std::vector<int32_t>& v2c, const std
     if ((int)cur.size() > kTileCellCap) CFEM_THROW(-1, "node valence exceeds tile capacity");
   }
   close_tile(no);
+  // T16 format: per tile the distinct external columns (ascending) and 16-bit tile-local column indices
+  {
+    const int ntl = (int)hm.tile_node.size() - 1;
+    hm.lc16.resize(hm.nnz);
+    hm.tile_extptr.assign(ntl + 1, 0);
+    std::vector<std::vector<int32_t>> ext(ntl);
+    int max_ext = 0;
+    bool overflow = false;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : max_ext) reduction(|| : overflow)
+    for (int t = 0; t < ntl; ++t) {
+      const int32_t a = hm.tile_node[t], b = hm.tile_node[t + 1];
+      const int32_t p0 = hm.rowptr[a], p1 = hm.rowptr[b];
+      std::vector<int32_t>& e = ext[t];
+      for (int32_t p = p0; p < p1; ++p) {
+        const int32_t col = hm.colidx[p];
+        if (col < a || col >= b) e.push_back(col);
+      }
+      std::sort(e.begin(), e.end());
+      e.erase(std::unique(e.begin(), e.end()), e.end());
+      if ((int)e.size() + kTileNodes > 65535) overflow = true;
+      max_ext = std::max(max_ext, (int)e.size());
+      for (int32_t p = p0; p < p1; ++p) {
+        const int32_t col = hm.colidx[p];
+        if (col >= a && col < b) hm.lc16[p] = (uint16_t)(col - a);
+        else hm.lc16[p] = (uint16_t)(kTileNodes + (std::lower_bound(e.begin(), e.end(), col) - e.begin()));
+      }
+    }
+    if (overflow) CFEM_THROW(-1, "tile has too many external columns for 16-bit local indices");
+    hm.max_tile_ext = max_ext;
+    for (int t = 0; t < ntl; ++t) hm.tile_extptr[t + 1] = hm.tile_extptr[t] + (int32_t)ext[t].size();
+    hm.tile_ext.resize(hm.tile_extptr[ntl]);
+    for (int t = 0; t < ntl; ++t) std::copy(ext[t].begin(), ext[t].end(), hm.tile_ext.begin() + hm.tile_extptr[t]);
+  }
   // interior tiles (no ghost column in any row) first: SpMV-type kernels start on them while the
   // neighbours' halo values are still in flight
   const int nt = (int)hm.tile_node.size() - 1;

@@ -265,7 +265,9 @@ int cfem_step_euler(cfem_ctx* ctx, const cfem_step_params* p, int n_steps, cfem_
  * algorithmic bytes one launch moves. */
 enum { CFEM_KERNEL_SPMV = 0, CFEM_KERNEL_ASM_RESIDUAL = 1, CFEM_KERNEL_ASM_JACOBIAN = 2,
        CFEM_KERNEL_RV_EPSILON = 3, CFEM_KERNEL_ASM_RV_RHS = 4, CFEM_KERNEL_PCG_ITER = 5,
-       CFEM_KERNEL_COMM_ALLREDUCE = 6 /* 3-scalar all-reduce over the ranks */, CFEM_KERNEL_COMM_HALO = 7 /* full halo exchange of one field */ };
+       CFEM_KERNEL_COMM_ALLREDUCE = 6 /* 3-scalar all-reduce over the ranks */, CFEM_KERNEL_COMM_HALO = 7 /* full halo exchange of one field */,
+       CFEM_KERNEL_SPMV_SYSTEM = 8 /* SpMV with two fused dots on CFEM_MAT_SYSTEM (the BiCGStab kernel) */,
+       CFEM_KERNEL_CHEB_ITER = 9 /* one Chebyshev iteration on CFEM_MAT_MASS_BC */ };
 /* Bracket every kernel launch of the following calls with CUDA events (adds ~2 us
  * per launch; use on a separate pass, not on the timed one).  cfem_profile_end sums
  * the device time and launch count per category:
@@ -289,7 +291,11 @@ enum { CFEM_HM_N2U = 0, CFEM_HM_CELLS = 1, CFEM_HM_ROWPTR = 2, CFEM_HM_COLIDX = 
        /* partition (cfem_host_analyse_part): peers and halo lists of this rank */
        CFEM_HM_PEER_RANK = 11, CFEM_HM_SEND_PTR = 12, CFEM_HM_SEND_IDX = 13, CFEM_HM_RECV_OFF = 14,
        CFEM_HM_RECV_CNT = 15,
-       CFEM_HM_LAST_CELL = 16 /* per owned node: incident local cell with the highest caller index */ };
+       CFEM_HM_LAST_CELL = 16 /* per owned node: incident local cell with the highest caller index */,
+       /* T16 tile format of the SpMV-type kernels: per CSR entry a 16-bit tile-local column (< 256: row n0 + index of
+        * the same tile; otherwise 256 + position in the tile's ascending list of external columns) */
+       CFEM_HM_LC16 = 17 /* uint16 */, CFEM_HM_TILE_EXTPTR = 18, CFEM_HM_TILE_EXT = 19,
+       CFEM_HM_TILE_ORDER = 20 /* tiles without ghost columns first */ };
 int cfem_host_analyse(cfem_host_mesh** out, int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
                       const void* cells, int cell_index_bytes, int order);
 /* same, restricted to rank's part of a world-way partition (what cfem_create_distributed builds) */
@@ -297,7 +303,7 @@ int cfem_host_analyse_part(cfem_host_mesh** out, int rank, int world, int64_t n_
                            const double* x, int xdim, const void* cells, int cell_index_bytes, int order);
 /* what: 0 owned nodes, 1 local nodes (owned + ghosts), 2 global nodes, 3 local cells, 4 nnz of owned rows */
 int64_t cfem_host_info(const cfem_host_mesh* hm, int what);
-/* number of elements of array `what` (4-byte elements except CFEM_HM_IS_BND) */
+/* number of elements of array `what` (4-byte elements except CFEM_HM_IS_BND: 1 byte, CFEM_HM_LC16: 2 bytes) */
 int64_t cfem_host_size(const cfem_host_mesh* hm, int what);
 int cfem_host_copy(const cfem_host_mesh* hm, int what, void* dst);
 void cfem_host_free(cfem_host_mesh* hm);

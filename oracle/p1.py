@@ -29,6 +29,12 @@ _WA5 = (155.0 - _S15) / 1200.0
 _WB5 = (155.0 + _S15) / 1200.0
 
 
+# Column ordering of every sparse LU in the oracle.  The matrices here have a symmetric pattern (P1 graph), for which
+# minimum degree on A^T + A gives ~3x less fill and factorisation time than SuperLU's COLAMD default (1024^2 Burgers
+# Jacobian: 50 s vs 150 s); it plays the role of the nested-dissection ordering PETSc's LU uses in the reference.
+LU_ORDERING = "MMD_AT_PLUS_A"
+
+
 def _orbit(a):
     c = 1.0 - 2.0 * a
     return [(c, a, a), (a, c, a), (a, a, c)]
@@ -215,5 +221,5 @@ def nodal_h(x, cells, solve=None):
     b = assemble_vector(cells, np.repeat((hk * area / 3.0)[:, None], 3, axis=1), n)
     M = mass_matrix(x, cells)
     if solve is None:
-        return splu(M.tocsc()).solve(b)
+        return splu(M.tocsc(), permc_spec=LU_ORDERING).solve(b)
     return solve(M, b)

@@ -112,7 +112,7 @@ class Mesh:
         key = ("M", bc)
         if key not in self._lu:
             A = p1.apply_bc_matrix(self.M, self.bnd) if bc else self.M
-            self._lu[key] = splu(A.tocsc())
+            self._lu[key] = splu(A.tocsc(), permc_spec=p1.LU_ORDERING)
         return self._lu[key]
 
 
@@ -195,7 +195,7 @@ def newton(F_fn, J_fn, x, bc_dofs, bc_vals, rtol, atol=1e-10, max_it=50,
     def solve(xx, b):
         if lu_cache is not None and "lu" in lu_cache:
             return lu_cache["lu"].solve(b)
-        lu = splu(p1.apply_bc_matrix(J_fn(xx), bc_dofs).tocsc())
+        lu = splu(p1.apply_bc_matrix(J_fn(xx), bc_dofs).tocsc(), permc_spec=p1.LU_ORDERING)
         if lu_cache is not None:
             lu_cache["lu"] = lu
         return lu.solve(b)
@@ -389,7 +389,7 @@ def advection_solve(m: Mesh, A, B, u_n, g=0.0):
     if np.any(gv != 0.0):
         b = b - A.tocsc()[:, m.bnd] @ gv
     b[m.bnd] = gv
-    return splu(p1.apply_bc_matrix(A, m.bnd).tocsc()).solve(b)
+    return splu(p1.apply_bc_matrix(A, m.bnd).tocsc(), permc_spec=p1.LU_ORDERING).solve(b)
 
 
 def run_advection(x, cells, dt, num_steps, Cvel=0.25, Crv=1.0, u0=None, w=None, h=None,
@@ -439,7 +439,7 @@ def run_advection_rk4(x, cells, dt, num_steps, u0=None, w=None):
     u = advection_initial_condition(x) if u0 is None else np.array(u0, dtype=np.float64)
     w = advection_velocity(x) if w is None else w
     C = p1.assemble_matrix(m.cells, p1.convection_elements(m.area, m.grad, np.asarray(w).reshape(-1, 2)[m.cells]), m.n)
-    lu = splu(p1.apply_bc_matrix(m.M, m.bnd).tocsc())
+    lu = splu(p1.apply_bc_matrix(m.M, m.bnd).tocsc(), permc_spec=p1.LU_ORDERING)
 
     def k_of(v):
         b = -(C @ v)

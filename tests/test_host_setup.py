@@ -111,6 +111,33 @@ def test_host_analysis(name, order):
     assert abs(Mu - ref).max() <= 1e-15 * abs(ref).max()
 
 
+@pytest.mark.parametrize("name", ["right", "jittered_permuted", "delaunay"])
+@pytest.mark.parametrize("order", [L.ORDER_HILBERT, L.ORDER_NATURAL])
+@pytest.mark.parametrize("world", [1, 3])
+def test_t16_tile_format_decodes_to_the_csr_columns(name, order, world):
+    """The 16-bit tile-local columns of the SpMV-type kernels: index < 256 is a row of the same tile, otherwise
+    256 + position in the tile's ascending external-column list; decoding gives colidx back bit for bit, external
+    lists hold no own row and no duplicate, and ghost columns (>= n_owned) sort last."""
+    x, c = CASES[name]() if name != "right" else meshes.rectangle(40, 37)
+    for rank in range(world):
+        hm = L.host_analyse(x, c, order, rank=rank, world=world)
+        rp, ci, lc = hm["rowptr"], hm["colidx"], hm["lc16"].astype(np.int64)
+        tn, ep, ext = hm["tile_node"], hm["tile_extptr"], hm["tile_ext"]
+        assert lc.size == ci.size == hm["nnz"] and ep.size == tn.size and ep[-1] == ext.size
+        for t in range(tn.size - 1):
+            a, b = tn[t], tn[t + 1]
+            e = ext[ep[t]:ep[t + 1]]
+            assert np.all(np.diff(e) > 0) and not np.any((e >= a) & (e < b))
+            p0, p1_ = rp[a], rp[b]
+            loc = lc[p0:p1_]
+            own = loc < 256
+            dec = np.where(own, a + loc, e[np.clip(loc - 256, 0, max(e.size - 1, 0))] if e.size else a + loc)
+            assert np.array_equal(dec, ci[p0:p1_])
+            assert np.all(loc[~own] - 256 < e.size)
+        order_t = hm["tile_order"]
+        assert sorted(order_t.tolist()) == list(range(tn.size - 1))
+
+
 @pytest.mark.parametrize("world", [1, 3])
 def test_last_cell_is_highest_numbered_incident_cell(world):
     """RV_cell.py:190-192 writes each cell's viscosity to its dofs in cell order: a node keeps the value
