@@ -43,6 +43,7 @@ class StepParams(C.Structure):
         ("newton_max_it", C.c_int32), ("solver", C.c_int32),
         ("lin_rtol", C.c_double), ("lin_max_it", C.c_int32), ("bc_kind", C.c_int32),
         ("bc_value", C.c_double), ("residual_bc", C.c_int32), ("mass_solver", C.c_int32),
+        ("mass_rtol", C.c_double),
     ]
 
 
@@ -84,6 +85,7 @@ SIGNATURES = {
     "cfem_num_dirichlet": (_L, [_P]),
     "cfem_num_tiles": (_L, [_P]),
     "cfem_device_bytes": (_L, [_P]),
+    "cfem_device_limits": (_I, [_I, _P]),
     "cfem_get_csr_pattern": (_I, [_P, _P, _P]),
     "cfem_get_boundary_dofs": (_I, [_P, _P]),
     "cfem_set_dirichlet": (_I, [_P, _P, _L]),
@@ -126,6 +128,13 @@ HM_ARRAYS = {"n2u": 0, "cells": 1, "rowptr": 2, "colidx": 3, "v2c_ptr": 4, "v2c_
              "tile_cellptr": 7, "tile_cells": 8, "is_bnd": 9, "bnd_user": 10, "peer_rank": 11, "send_ptr": 12,
              "send_idx": 13, "recv_off": 14, "recv_cnt": 15, "last_cell": 16, "lc16": 17, "tile_extptr": 18,
              "tile_ext": 19, "tile_order": 20}
+
+
+def device_limits(device=0):
+    """{'l2_bytes', 'persisting_l2_max', 'access_window_max', 'sm_count'} of a CUDA device."""
+    out = (C.c_int64 * 4)()
+    check(load().cfem_device_limits(int(device), out))
+    return dict(zip(("l2_bytes", "persisting_l2_max", "access_window_max", "sm_count"), [int(v) for v in out]))
 
 
 def host_analyse(x, cells, order=ORDER_HILBERT, rank=0, world=1):

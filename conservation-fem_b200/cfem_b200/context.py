@@ -363,7 +363,7 @@ def _flux(flux):
 
 def step_params(flux, dt, Cvel, Crv, scheme="bdf2", newton_rtol=1e-4, newton_atol=1e-10, newton_max_it=100,
                 solver="bicgstab", lin_rtol=1e-13, lin_max_it=2000, bc_kind="constant", bc_value=0.0,
-                residual_bc=True, mass_solver="chebyshev"):
+                residual_bc=True, mass_solver="chebyshev", mass_rtol=0.0):
     p = L.StepParams()
     p.flux = _flux(flux)
     p.scheme = L.BDF2 if scheme in ("bdf2", 2) else L.BDF1
@@ -375,4 +375,5 @@ def step_params(flux, dt, Cvel, Crv, scheme="bdf2", newton_rtol=1e-4, newton_ato
     p.bc_value = float(bc_value)
     p.residual_bc = int(bool(residual_bc))
     p.mass_solver = 100 + L.SOLVER_PCG if mass_solver == "pcg" else 0
+    p.mass_rtol = float(mass_rtol)
     return p

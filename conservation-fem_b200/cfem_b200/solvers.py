@@ -84,13 +84,13 @@ def advection_dt(w, hmax, CFL=0.5):
 
 # ---- loops ------------------------------------------------------------------------
 def _run_scalar(flux, domain, u0, dt, num_steps, Cvel, Crv, bc_kind, bc_value, scheme, newton_rtol,
-                solver, lin_rtol, device, h, return_stats, xdmf=None, write_every=1):
+                solver, lin_rtol, device, h, return_stats, xdmf=None, write_every=1, mass_rtol=0.0):
     ctx = domain if isinstance(domain, Context) else Context.for_domain(domain, device=device)
     u0 = _interpolate(ctx, u0)
     h = ctx.nodal_h() if h is None else _interpolate(ctx, h)
     ctx.state_set(uh=u0, u_n=u0, u_old=u0, u_oo=u0, RH=np.zeros(ctx.n), h=h, t=0.0)
     p = step_params(flux, dt, Cvel, Crv, scheme=scheme, newton_rtol=newton_rtol, solver=solver,
-                    lin_rtol=lin_rtol, bc_kind=bc_kind, bc_value=bc_value)
+                    lin_rtol=lin_rtol, bc_kind=bc_kind, bc_value=bc_value, mass_rtol=mass_rtol)
     if xdmf is None:
         stats = ctx.step_scalar(p, num_steps)
     else:
@@ -125,16 +125,16 @@ def _run_scalar(flux, domain, u0, dt, num_steps, Cvel, Crv, bc_kind, bc_value, s
 
 def solve_kpp(domain, initial_condition=kpp_initial_condition, dt=0.01, num_steps=100, Cvel=0.5, Crv=4.0,
               bc_value=np.pi / 4, scheme="bdf2", newton_rtol=1e-4, solver="bicgstab", lin_rtol=1e-13,
-              device=0, h=None, return_stats=False, xdmf=None, write_every=1):
+              device=0, h=None, return_stats=False, xdmf=None, write_every=1, mass_rtol=0.0):
     """KPP rotating wave, BDF2-residual RV + Crank-Nicolson Newton (``KPP_exact.py``).  ``xdmf``: path of an
     XDMF time series to write (``KPP_exact.py:108-109,165``), one frame every ``write_every`` steps."""
     return _run_scalar(L.FLUX_KPP, domain, initial_condition, dt, num_steps, Cvel, Crv, "constant", bc_value,
-                       scheme, newton_rtol, solver, lin_rtol, device, h, return_stats, xdmf, write_every)
+                       scheme, newton_rtol, solver, lin_rtol, device, h, return_stats, xdmf, write_every, mass_rtol)
 
 
 def solve_burgers(domain, initial_condition=burgers_initial_condition, dt=None, num_steps=None, Cvel=0.5,
                   Crv=10.0, CFL=0.5, T=0.5, scheme="bdf2", newton_rtol=1e-4, solver="bicgstab",
-                  lin_rtol=1e-13, device=0, h=None, return_stats=False, xdmf=None, write_every=1):
+                  lin_rtol=1e-13, device=0, h=None, return_stats=False, xdmf=None, write_every=1, mass_rtol=0.0):
     """2-D inviscid Burgers Riemann problem with exact Dirichlet data (``Exact_Burger_RV.py``).
 
     ``dt=None`` reproduces ``dt = CFL*min(h_CG)``, ``num_steps = ceil(T/dt)`` (``:105-109``).
@@ -146,7 +146,7 @@ def solve_burgers(domain, initial_condition=burgers_initial_condition, dt=None, 
     if num_steps is None:
         num_steps = int(np.ceil(T / dt))
     return _run_scalar(L.FLUX_BURGERS, ctx, initial_condition, dt, num_steps, Cvel, Crv, "burgers_exact", 0.0,
-                       scheme, newton_rtol, solver, lin_rtol, device, h, return_stats, xdmf, write_every)
+                       scheme, newton_rtol, solver, lin_rtol, device, h, return_stats, xdmf, write_every, mass_rtol)
 
 
 def solve_burgers_si(domain, initial_condition=burgers_initial_condition, dt=None, num_steps=None, Cm=0.5,

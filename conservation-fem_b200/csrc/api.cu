@@ -341,7 +341,7 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   c->stage[1] = dalloc<double>(c, nn);
   c->stage[2] = dalloc<double>(c, 2 * nn);
   c->stage[3] = c->stage[2] + nn;
-  c->partials = dalloc<double>(c, 8 * (int64_t)kMaxPartials);
+  c->partials = dalloc<double>(c, 12 * (int64_t)kMaxPartials);   // slots 0..7 named in linalg.cu, 5..8 = the four dots of Ep16BiT
   c->partials12 = dalloc<double>(c, 12 * (int64_t)kMaxPartials);
   c->scalars = dalloc<double>(c, 32);
   c->status = dalloc<int32_t>(c, 8);
@@ -418,6 +418,16 @@ int64_t cfem_num_boundary(const cfem_ctx* c) { return (int64_t)c->hm.bnd_user_so
 int64_t cfem_num_dirichlet(const cfem_ctx* c) { return c->nbc_user; }
 int64_t cfem_num_tiles(const cfem_ctx* c) { return c->dm.ntiles; }
 int64_t cfem_device_bytes(const cfem_ctx* c) { return c->bytes; }
+int cfem_device_limits(int device, int64_t out[4]) {
+  API_BEGIN
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  out[0] = prop.l2CacheSize;
+  out[1] = prop.persistingL2CacheMaxSize;
+  out[2] = prop.accessPolicyMaxWindowSize;
+  out[3] = prop.multiProcessorCount;
+  API_END
+}
 
 int cfem_get_csr_pattern(cfem_ctx* c, int32_t* rowptr, int32_t* colidx) {
   API_BEGIN
@@ -730,6 +740,7 @@ static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps,
       d_bc_user = c->stage[2];
     }
   }
+  const double mass_rtol = p->mass_rtol > 0.0 ? p->mass_rtol : p->lin_rtol;
   double* b = c->wk[8];
   double* F = c->wk[8];
   double* dx = c->wk[9];
@@ -743,7 +754,7 @@ static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps,
       // (a-3) residual projection  M_bc RH = b
       launch_rv_rhs(c, p->flux, p->scheme, p->dt, c->u_n, c->u_old, c->u_oo, nullptr, true, b, c->fluxn);
       fluxn = c->fluxn;
-      SolveResult rm = mass_solve(c, p->mass_solver, c->mat[CFEM_MAT_MASS_BC], b, c->RH, p->lin_rtol, p->lin_max_it, &c->pcg_predict);
+      SolveResult rm = mass_solve(c, p->mass_solver, c->mat[CFEM_MAT_MASS_BC], b, c->RH, mass_rtol, p->lin_max_it, &c->pcg_predict);
       if (!rm.converged) CFEM_THROW(-3, "step_scalar: residual PCG did not converge");
       st.mass_iterations += rm.iters;
       // (a-4) nodal viscosity
@@ -772,6 +783,10 @@ static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps,
       const bool guess = use_guess && it == 0 && c->dx_guess_valid;
       if (guess) launch_copy(c, dx, c->dx_guess, nn);
       else launch_fill(c, dx, 0.0, nn);
+      // Dirichlet rows of J are identity rows and their columns are lifted into F: dx = F there, exactly.  Starting
+      // from it keeps those rows out of the iteration (zero residual, decoupled), so uh - dx lands on g to the bit
+      // like the reference's LU does.
+      launch_copy_indexed(c, dx, F, c->d_bc_nodes, c->nbc);
       SolveResult rk = run_solver(c, p->solver, J, F, dx, p->lin_rtol, 0.0, p->lin_max_it, &c->krylov_predict);
       if (!rk.converged) CFEM_THROW(-3, "step_scalar: Krylov solve did not converge (relres " + std::to_string(rk.relres) + ")");
       st.krylov_iterations += rk.iters;
@@ -850,6 +865,7 @@ int cfem_step_advection(cfem_ctx* c, const cfem_step_params* p, int n_steps, int
   CUDA_OK(cudaEventCreate(&ev0));
   CUDA_OK(cudaEventCreate(&ev1));
   CUDA_OK(cudaEventRecord(ev0, c->stream));
+  const double mass_rtol = p->mass_rtol > 0.0 ? p->mass_rtol : p->lin_rtol;
   double* b = c->wk[8];
   Matrix& A = c->mat[CFEM_MAT_SYSTEM];
   launch_bc_values(c, CFEM_BC_CONSTANT, p->bc_kind == CFEM_BC_CONSTANT ? p->bc_value : 0.0, 0.0, nullptr, c->g);
@@ -860,7 +876,7 @@ int cfem_step_advection(cfem_ctx* c, const cfem_step_params* p, int n_steps, int
       // (a-3) BDF1 residual projection, RV_node.py:209-214
       launch_rv_rhs(c, CFEM_FLUX_ADVECTION, CFEM_BDF1, p->dt, c->u_n, c->u_old, nullptr, c->w, p->residual_bc != 0, b, nullptr);
       SolveResult rm = mass_solve(c, p->mass_solver, c->mat[p->residual_bc ? CFEM_MAT_MASS_BC : CFEM_MAT_MASS], b, c->RH,
-                                  p->lin_rtol, p->lin_max_it, &c->pcg_predict);
+                                  mass_rtol, p->lin_max_it, &c->pcg_predict);
       if (!rm.converged) CFEM_THROW(-3, "step_advection: residual PCG did not converge");
       st.mass_iterations += rm.iters;
       // (a-5) nodal viscosity

@@ -5,6 +5,7 @@
 // The reference has no working parallel path of its own (its Utils loops are not MPI-safe,
 // SURVEY.md section 1); this layer replaces dolfinx's scatter_forward / ghostUpdate calls
 // (Code/Linear_advection/RV_node.py:241,246) and PETSc's parallel dot products.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -95,7 +96,11 @@ void comm_init(cfem_ctx* c, int rank, int world, const void* id128) {
   c->nccl_comm = it->second;
 }
 
-void comm_destroy(cfem_ctx* c) { c->nccl_comm = nullptr; }  // communicators are process-lifetime
+void comm_destroy_p2p(cfem_ctx* c);
+void comm_destroy(cfem_ctx* c) {
+  comm_destroy_p2p(c);
+  c->nccl_comm = nullptr;  // communicators are process-lifetime (cached by unique id)
+}
 
 // ---------------------------------------------------------------- peer-memory path (NVLink, CUDA IPC)
 // NCCL's latency (~15 us per grouped send/recv or all-reduce) dominates at ~1M dofs per GPU, where
@@ -107,8 +112,30 @@ void comm_destroy(cfem_ctx* c) { c->nccl_comm = nullptr; }  // communicators are
 // neighbour because each exchange waits for the neighbour's previous one.  Kernels on DIFFERENT
 // GPUs wait on one another; nothing waits on another kernel of the same GPU.  Spins are bounded
 // (~30 s) and raise an error flag instead of hanging.
+// A cudaMalloc'ed mailbox may be a sub-allocation of a larger block: its IPC handle then names the BLOCK, so two
+// contexts of one process can hold mailboxes with the same handle, and a handle can be opened only once per process.
+// Opened blocks are therefore cached process-wide (reference counted) and every rank publishes its mailbox as
+// (handle of the block, offset of the mailbox inside it).
+struct IpcBlock { void* base; int refs; };
+static std::map<std::string, IpcBlock>& ipc_cache() { static std::map<std::string, IpcBlock> m; return m; }
+static void* ipc_open(const cudaIpcMemHandle_t& h) {
+  const std::string key((const char*)&h, sizeof(h));
+  auto it = ipc_cache().find(key);
+  if (it != ipc_cache().end()) { it->second.refs++; return it->second.base; }
+  void* ptr = nullptr;
+  CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  ipc_cache()[key] = IpcBlock{ptr, 1};
+  return ptr;
+}
+static void ipc_close(const std::string& key) {
+  auto it = ipc_cache().find(key);
+  if (it == ipc_cache().end()) return;
+  if (--it->second.refs == 0) { cudaIpcCloseMemHandle(it->second.base); ipc_cache().erase(it); }
+}
+
 struct P2P {
   P2PDev d;
+  std::vector<std::string> opened;   // keys of the peer blocks this context holds a reference to
   unsigned long long halo_seq = 0, red_seq = 0;
   int32_t* d_send_ptr = nullptr;
   int32_t* d_peer_rank = nullptr;
@@ -319,12 +346,25 @@ static void p2p_setup(cfem_ctx* c) {
   // ---- all-gather the IPC handles and the landing offsets (NCCL is the setup plumbing)
   cudaIpcMemHandle_t mine;
   CUDA_OK(cudaIpcGetMemHandle(&mine, box));
+  int64_t box_offset = 0;   // of the mailbox inside the allocation the handle names
+  {
+    // driver entry point through the runtime: the library must load on machines without libcuda (CPU-only tests)
+    typedef CUresult (*GetRange)(CUdeviceptr*, size_t*, CUdeviceptr);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_OK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (!fn || ((GetRange)fn)(&base, &size, (CUdeviceptr)box) != CUDA_SUCCESS) CFEM_THROW(-5, "cuMemGetAddressRange failed for the mailbox");
+    box_offset = (int64_t)((CUdeviceptr)box - base);
+  }
   std::vector<int32_t> land(world, -1);  // where rank q's values land in MY ghost segment
   for (int k = 0; k < npeer; ++k) land[hm.peer_rank[k]] = hm.recv_off[k] - (int32_t)hm.n_owned;
-  const size_t rec = sizeof(cudaIpcMemHandle_t) + world * sizeof(int32_t);
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + sizeof(int64_t) + world * sizeof(int32_t);
   std::vector<char> sendrec(rec), allrec(rec * world);
   memcpy(sendrec.data(), &mine, sizeof(mine));
-  memcpy(sendrec.data() + sizeof(mine), land.data(), world * sizeof(int32_t));
+  memcpy(sendrec.data() + sizeof(mine), &box_offset, sizeof(int64_t));
+  memcpy(sendrec.data() + sizeof(mine) + sizeof(int64_t), land.data(), world * sizeof(int32_t));
   char *dsend = nullptr, *drecv = nullptr;
   CUDA_OK(cudaMalloc((void**)&dsend, rec));
   CUDA_OK(cudaMalloc((void**)&drecv, rec * world));
@@ -343,16 +383,17 @@ static void p2p_setup(cfem_ctx* c) {
   for (int q = 0; q < world; ++q) {
     if (q == rank) { d.rank_base[q] = (char*)box; continue; }
     cudaIpcMemHandle_t h;
+    int64_t off = 0;
     memcpy(&h, allrec.data() + q * rec, sizeof(h));
-    void* ptr = nullptr;
-    CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    d.rank_base[q] = (char*)ptr;
+    memcpy(&off, allrec.data() + q * rec + sizeof(h), sizeof(int64_t));
+    d.rank_base[q] = (char*)ipc_open(h) + off;
+    pp->opened.emplace_back((const char*)&h, sizeof(h));
   }
   for (int k = 0; k < npeer; ++k) {
     const int q = hm.peer_rank[k];
     d.peer_base[k] = d.rank_base[q];
     d.peer_rank[k] = q;
-    const int32_t* their_land = (const int32_t*)(allrec.data() + q * rec + sizeof(cudaIpcMemHandle_t));
+    const int32_t* their_land = (const int32_t*)(allrec.data() + q * rec + sizeof(cudaIpcMemHandle_t) + sizeof(int64_t));
     d.dst_off[k] = their_land[rank];
     if (d.dst_off[k] < 0 && hm.send_ptr[k + 1] > hm.send_ptr[k]) CFEM_THROW(-5, "inconsistent halo lists between ranks");
   }
@@ -378,6 +419,18 @@ static void p2p_setup(cfem_ctx* c) {
   NCCL_OK(nccl().AllReduce(tmp, tmp, 1, ncclDouble, ncclSum, comm, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   c->p2p = pp;
+}
+
+// Peer mappings are released (reference counted per process) and the pinned error flag freed; the mailbox itself
+// is part of c->allocs.  The caller destroys contexts collectively (every rank leaves its time loop before any
+// rank frees a mailbox the others may still map) -- cfem_destroy documents that.
+void comm_destroy_p2p(cfem_ctx* c) {
+  if (!c->p2p) return;
+  P2P* pp = (P2P*)c->p2p;
+  for (const std::string& key : pp->opened) ipc_close(key);
+  if (pp->h_error) cudaFreeHost(pp->h_error);
+  delete pp;
+  c->p2p = nullptr;
 }
 
 void comm_setup_exchange(cfem_ctx* c) {
@@ -520,6 +573,20 @@ int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int*
   NCCL_OK(nccl().GroupEnd());
   c->allreduces++;
   return 1;
+}
+
+bool fin_available(const cfem_ctx* c) { return c->world == 1 || c->p2p != nullptr; }
+
+Fin make_fin(cfem_ctx* c) {
+  Fin f;
+  f.counter = (unsigned int*)(c->status + 4);   // zeroed at creation, reset by the last CTA of every launch
+  if (c->world > 1 && c->p2p) {
+    P2P* pp = (P2P*)c->p2p;
+    f.dev = pp->d_dev;
+    f.seq = ++pp->red_seq;
+    c->allreduces++;
+  }
+  return f;
 }
 
 int allreduce_sum1(cfem_ctx* c, double* slot, int npart) {

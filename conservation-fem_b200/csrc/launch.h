@@ -43,6 +43,8 @@ void launch_scatter(cfem_ctx* c, const double* src, const int32_t* idx, double* 
 void launch_gather2(cfem_ctx* c, const double2* src, const int32_t* idx, double2* dst, int64_t n);
 void launch_fill(cfem_ctx* c, double* dst, double v, int64_t n);
 void launch_copy(cfem_ctx* c, double* dst, const double* src, int64_t n);
+// dst[idx[k]] = src[idx[k]], k < n
+void launch_copy_indexed(cfem_ctx* c, double* dst, const double* src, const int32_t* idx, int64_t n);
 // x -= dx
 void launch_sub(cfem_ctx* c, double* x, const double* dx, int64_t n);
 struct SolveResult { int iters; double relres; bool converged; };
@@ -79,6 +81,11 @@ GhostSrc halo_push(cfem_ctx* c, double* v, bool gated, bool in_consumer = false)
 // local reduce of each partial array to its element 0 + all-reduce; returns the partial count to use after
 int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int* ops /*0 sum,1 min,2 max*/, int npart);
 int allreduce_sum1(cfem_ctx* c, double* slot, int npart);
+// in-kernel finalisation of reductions (p2p.cuh): descriptor for the NEXT producer launch -- takes a fresh all-reduce
+// sequence number in a distributed context; fin_available: one GPU, or the peer-memory path is up
+struct Fin;
+Fin make_fin(cfem_ctx* c);
+bool fin_available(const cfem_ctx* c);
 
 // ---- RV (rv.cu) ------------------------------------------------------------------
 // sum / min / max of v -> c->scalars[0..2] (device), no host sync

@@ -1,6 +1,6 @@
 // Device-side view of the peer-memory exchange (comm.cu) shared with the SpMV-type kernels.
 #pragma once
-#include "internal.h"
+#include "device_utils.cuh"
 
 namespace cfem {
 
@@ -74,6 +74,102 @@ __device__ __forceinline__ void ghost_wait(const GhostSrc& g) {
     wait_flag((const volatile unsigned long long*)(g.flags + 8 * g.peer_rank[threadIdx.x]), g.seq, g.error);
   __syncthreads();
   __threadfence_system();
+}
+
+// ---- in-kernel finalisation of reductions -------------------------------------------------------------------------
+// A kernel whose CTAs each produce partial sums hands them to fin_reduce: the LAST CTA to arrive (ticket counter)
+// adds the partials up in a fixed order and -- in a distributed context -- exchanges the totals with every rank
+// through the tagged-word slots of the peer mailboxes (same protocol as k_p2p_allreduce_ll) and folds them in rank
+// order, so all ranks end up with bitwise identical scalars.  The consumer kernel then reads ready scalars: no
+// finalise launch, no all-reduce launch, no per-CTA re-reduction of ~1000 partials in the consumer's prologue.
+struct Fin {
+  unsigned int* counter = nullptr;   // device ticket counter, zero between launches (null: finalisation off)
+  const P2PDev* dev = nullptr;       // non-null: all-reduce over the ranks
+  unsigned long long seq = 0;        // all-reduce sequence number of this launch (same on every rank)
+};
+template <int NS>
+struct Slots { double* p[NS]; };
+
+// sums[k] (shared memory) <- sum over ranks, rank order; called by all threads of ONE CTA (blockDim.x >= NS * world)
+template <int NS>
+__device__ __forceinline__ void cta_allreduce(const P2PDev* __restrict__ a, const unsigned long long seq, double* sums) {
+  __shared__ double recv[NS][kMaxWorld];
+  const int world = a->world, rank = a->rank;
+  const int parity = (int)(seq & 1);
+  const unsigned int tag = (unsigned int)seq;
+  const size_t ll_off = kFlagBytes + kRedBytes;
+  if ((int)threadIdx.x < NS * world) {
+    const int slot = threadIdx.x / world, q = threadIdx.x - slot * world;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(sums[slot]);
+    volatile unsigned long long* dst = (volatile unsigned long long*)(a->rank_base[q] + ll_off) +
+                                       (((size_t)parity * kMaxWorld + rank) * 8 + slot) * 2;
+    dst[0] = (bits & 0xffffffff00000000ull) | tag;
+    dst[1] = (bits << 32) | tag;
+    const volatile unsigned long long* src = (const volatile unsigned long long*)(a->local + ll_off) +
+                                             (((size_t)parity * kMaxWorld + q) * 8 + slot) * 2;
+    const long long t0 = clock64();
+    unsigned long long hi = src[0], lo = src[1];
+    while ((unsigned int)hi != tag || (unsigned int)lo != tag) {
+      if (clock64() - t0 > 60000000000LL) { *a->error = 1; break; }
+      hi = src[0]; lo = src[1];
+    }
+    recv[slot][q] = __longlong_as_double((long long)((hi & 0xffffffff00000000ull) | (lo >> 32)));
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < NS) {
+    double r = recv[threadIdx.x][0];
+    for (int q = 1; q < world; ++q) r += recv[threadIdx.x][q];
+    sums[threadIdx.x] = r;
+  }
+  __syncthreads();
+}
+
+// Every thread of every participating CTA calls this after thread 0 of the CTA has stored part.p[k][cta].
+// Returns true in all threads of the last CTA, with sums[0..NS) (shared memory) holding the global totals.
+template <int NS>
+__device__ __forceinline__ bool fin_reduce(const Fin& fin, const Slots<NS>& part, const int ncta, double* red /*>= 9*/,
+                                           double* sums /*>= NS, shared*/) {
+  __shared__ bool fin_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                               // this CTA's partials are visible before its ticket is
+    const unsigned int t = atomicAdd(fin.counter, 1u);
+    fin_last = (t == (unsigned int)ncta - 1u);
+  }
+  __syncthreads();
+  if (!fin_last) return false;
+  __threadfence();
+  // all NS slots in one pass: the loads of the slots are independent, the NS tree reductions share their barriers.
+  // Per slot the order is the one reduce_partials uses (thread-strided partial sums, shuffle tree, warp order).
+  double s[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s[k] = 0.0;
+  for (int i = threadIdx.x; i < ncta; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) s[k] += __ldcg(part.p[k] + i);
+  }
+  {
+    __shared__ double wsum[NS][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      const double w = warp_sum(s[k]);
+      if (lane == 0) wsum[k][wid] = w;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        double t = lane < (kBlock / 32) ? wsum[k][lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) sums[k] = t;
+      }
+    }
+  }
+  __syncthreads();
+  if (fin.dev) cta_allreduce<NS>(fin.dev, fin.seq, sums);
+  if (threadIdx.x == 0) *fin.counter = 0;          // ready for the next launch (stream ordered)
+  return true;
 }
 
 }  // namespace cfem

@@ -98,6 +98,9 @@ int64_t cfem_num_dirichlet(const cfem_ctx* ctx);
 int64_t cfem_num_tiles(const cfem_ctx* ctx);
 /* bytes of device memory the context holds */
 int64_t cfem_device_bytes(const cfem_ctx* ctx);
+/* L2 facts of `device`: out[0] L2 bytes, out[1] largest persisting set-aside, out[2] largest access-policy window,
+ * out[3] SM count.  (The solvers keep the matrix of a solve in persisting L2 lines; CFEM_L2PERSIST=0 turns that off.) */
+int cfem_device_limits(int device, int64_t out[4]);
 
 /* Node patches / sparsity pattern in caller numbering, columns ascending.
  * rowptr: n_nodes+1, colidx: nnz (host).          SI.py:12-28 */
@@ -181,12 +184,14 @@ typedef struct cfem_step_params {
   double newton_atol;    /* 1e-10  dolfinx NewtonSolver default                  */
   int32_t newton_max_it; /* 100    KPP_exact.py:149                              */
   int32_t solver;        /* CFEM_SOLVER_* for the non-symmetric systems          */
-  double lin_rtol;       /* Krylov ||r||/||b||, stands in for LU (default 1e-13) */
+  double lin_rtol;       /* Krylov ||D^-1 r||/||D^-1 b||, stands in for LU (default 1e-13) */
   int32_t lin_max_it;
   int32_t bc_kind;       /* CFEM_BC_*                                            */
   double bc_value;       /* CFEM_BC_CONSTANT                                     */
   int32_t residual_bc;   /* advection: project the residual with bc (RV_node.py:213) or without (RV_node_convergence.py:188) */
   int32_t mass_solver;   /* CFEM_SOLVER_CHEBYSHEV (default, 0 maps to it) or CFEM_SOLVER_PCG+100 */
+  double mass_rtol;      /* tolerance of the residual-projection (mass) solves; 0 = lin_rtol.  All tolerances are on the
+                            row-equilibrated residual ||D^-1 r|| / ||D^-1 b|| (D = diag), see DESIGN.md section 4 */
 } cfem_step_params;
 
 typedef struct cfem_step_stats {

@@ -19,6 +19,9 @@ from cfem_b200 import solvers as GS  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-10
+# solver tolerances (on the row-equilibrated residual): the library default, and what bench.py times with
+SETTINGS = [pytest.param(dict(lin_rtol=1e-13), id="default_1e-13"),
+            pytest.param(dict(lin_rtol=1e-11, mass_rtol=1e-11), id="bench_1e-11")]
 
 
 def rel(a, b):
@@ -43,11 +46,12 @@ def test_config0_advection_100x100_50_steps():
     assert rel(st["eps"], g["eps"]) < 1e-8
 
 
-def test_config1_burgers_1024x1024_3_steps():
+@pytest.mark.parametrize("tols", SETTINGS)
+def test_config1_burgers_1024x1024_3_steps(tols):
     g = _load("config1_burgers_1024x1024_3steps.npz")
     n = int(g["n"])
     x, c = meshes.rectangle(n, n)
-    uh, st = GS.solve_burgers((x, c), dt=float(g["dt"]), num_steps=int(g["steps"]), return_stats=True)
+    uh, st = GS.solve_burgers((x, c), dt=float(g["dt"]), num_steps=int(g["steps"]), return_stats=True, **tols)
     idx = g["index"]
     u = uh.x.array
     assert rel(u[idx], g["uh"]) < TOL
@@ -58,11 +62,12 @@ def test_config1_burgers_1024x1024_3_steps():
     assert rel(st["eps"][idx], g["eps"]) < 1e-8 and abs(np.linalg.norm(st["eps"]) / float(g["norm_eps"]) - 1) < 1e-8
 
 
-def test_config2_kpp_4M_cells_2_steps():
+@pytest.mark.parametrize("tols", SETTINGS)
+def test_config2_kpp_4M_cells_2_steps(tols):
     g = _load("config2_kpp_1448x1448_jittered_2steps.npz")
     n = int(g["n"])
     x, c = meshes.jittered(n, n, (-2.0, -2.0), (2.0, 2.0))
-    uh, st = GS.solve_kpp((x, c), dt=float(g["dt"]), num_steps=int(g["steps"]), return_stats=True)
+    uh, st = GS.solve_kpp((x, c), dt=float(g["dt"]), num_steps=int(g["steps"]), return_stats=True, **tols)
     idx = g["index"]
     u = uh.x.array
     assert rel(u[idx], g["uh"]) < TOL

@@ -28,7 +28,7 @@ def test_header_symbols_exported(lib):
 def test_struct_layouts_match_header(lib):
     import ctypes as C
 
-    assert C.sizeof(L.StepParams) == lib.cfem_struct_size(0) == 88
+    assert C.sizeof(L.StepParams) == lib.cfem_struct_size(0) == 96
     assert C.sizeof(L.StepStats) == lib.cfem_struct_size(1) == 80
 
 
