@@ -399,6 +399,7 @@ void cfem_destroy(cfem_ctx* c) {
   for (cudaEvent_t e : c->prof.ev) cudaEventDestroy(e);
   euler_free(c);
   smooth_plan_free(c);
+  persist_plan_free(c);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->stream) cudaStreamDestroy(c->stream);

@@ -575,6 +575,33 @@ int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int*
   return 1;
 }
 
+void persist_comm_args(cfem_ctx* c, const P2PDev** dev, const char** mailbox, size_t* halo_off, size_t* halo_stride,
+                       const int32_t** peer_rank, int* npeer, int** error, unsigned long long* halo_seq,
+                       unsigned long long* red_seq) {
+  *dev = nullptr; *mailbox = nullptr; *halo_off = 0; *halo_stride = 0; *peer_rank = nullptr; *npeer = 0; *error = nullptr;
+  *halo_seq = 0; *red_seq = 0;
+  if (c->world == 1 || !c->p2p) return;
+  P2P* pp = (P2P*)c->p2p;
+  *dev = pp->d_dev;
+  *mailbox = pp->d.local;
+  *halo_off = pp->d.halo_off;
+  *halo_stride = pp->d.halo_stride;
+  *peer_rank = pp->d_peer_rank;
+  *npeer = pp->d.npeer;
+  *error = pp->d.error;
+  *halo_seq = pp->halo_seq;
+  *red_seq = pp->red_seq;
+}
+
+void persist_comm_advance(cfem_ctx* c, int64_t halo_exchanges, int64_t allreduces) {
+  if (c->world == 1 || !c->p2p) return;
+  P2P* pp = (P2P*)c->p2p;
+  pp->halo_seq += (unsigned long long)halo_exchanges;
+  pp->red_seq += (unsigned long long)allreduces;
+  c->halo_exchanges += halo_exchanges;
+  c->allreduces += allreduces;
+}
+
 bool fin_available(const cfem_ctx* c) { return c->world == 1 || c->p2p != nullptr; }
 
 Fin make_fin(cfem_ctx* c) {

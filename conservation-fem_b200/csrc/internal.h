@@ -195,6 +195,7 @@ struct cfem_ctx {
   size_t hot_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // MASS_BC vals | rowptr | lc16 | extptr | ext | SYSTEM vals | colidx | end
   size_t l2_setaside = 0;                // bytes of L2 set aside for persisting lines (0: feature off)
   size_t l2_max_window = 0;
+  void* persist_plan = nullptr;          // launch plan of the persistent BiCGStab kernel (persist.cu)
   int t16_grid = 0;                      // grid of the T16 tile kernels (occupancy x SMs, <= tiles), 0 = not sized yet
   int l2_window = 0;                     // matrix id whose window is currently attached to the stream, -1 none
 };

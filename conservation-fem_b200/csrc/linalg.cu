@@ -782,9 +782,10 @@ k_pcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const d
 }
 
 static bool poll_done(cfem_ctx* c, SolveResult& res) {
-  CUDA_OK(cudaMemcpyAsync(c->h_status, c->status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_status, c->status, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + S_RELRES, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (c->h_status[3]) CFEM_THROW(-5, "a grid barrier of the persistent solver timed out");
   res.iters = c->h_status[1];
   res.relres = c->h_pinned[0];
   res.converged = c->h_status[0] == 1;
@@ -1252,12 +1253,35 @@ static SolveResult bicgstab_merged(cfem_ctx* c, const Matrix& A, const double* b
   return res;
 }
 
+// whole iteration loop in one cooperative launch (persist.cu); the host syncs once, to learn the verdict
+static SolveResult bicgstab_persist(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
+                                    int max_it, int* predict) {
+  l2_prefer(c, A);
+  const int64_t n = c->dm.no;
+  double *r = c->wk[0], *rhat = c->wk[1], *p = c->wk[2], *v = c->wk[3], *t = c->wk[5];
+  const double rtol2 = rtol * rtol, atol2 = atol * atol;
+  spmv_dots<0>(c, A, x, v, nullptr, nullptr, nullptr, nullptr, false);
+  { ProfScope ps(c, PROF_KRYLOV_VEC);
+    launch_pdl(k_bm_init, vec_grid(c, n), kBlock, 0, c->stream, n, b, v, A.dinv, r, rhat, p, c->partials, c->scalars, c->status, rtol2, atol2, make_fin(c));
+    LAUNCHED(c); }
+  SolveResult res{0, 0.0, false};
+  { ProfScope ps(c, PROF_SPMV);   // the whole loop is charged to the SpMV category of the breakdown
+    launch_bicg_persist(c, A, rhat, x, r, p, v, t, rtol2, atol2, max_it); }
+  poll_done(c, res);
+  persist_comm_advance(c, 2 * (int64_t)res.iters, 3 * (int64_t)res.iters);
+  halo_exchange(c, x, 1);
+  if (predict) *predict = res.iters > 0 ? res.iters : 1;
+  return res;
+}
+
 SolveResult bicgstab(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol,
                      int max_it, int* predict) {
   // merged form: needs the staged tile kernels and in-kernel all-reduces (one GPU, or the peer-memory path);
   // CFEM_BICGSTAB=5k, CFEM_SPMV=stream and the NCCL fallback use the five-launch form
   static const bool want5 = getenv("CFEM_BICGSTAB") && std::string(getenv("CFEM_BICGSTAB")) == "5k";
   if (want5 || !use_t16() || !fin_available(c)) return bicgstab_5k(c, A, b, x, rtol, atol, max_it, predict);
+  // default: the persistent kernel; CFEM_BICGSTAB=merged keeps one launch per phase (four per iteration)
+  if (bicgstab_persist_available(c)) return bicgstab_persist(c, A, b, x, rtol, atol, max_it, predict);
   return bicgstab_merged(c, A, b, x, rtol, atol, max_it, predict);
 }
 

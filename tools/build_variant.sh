@@ -6,7 +6,7 @@ name=$1; shift
 root=$(cd "$(dirname "$0")/.." && pwd)
 src=$root/conservation-fem_b200/csrc
 tmp=$(mktemp -d)
-for f in setup.cpp assembly.cu linalg.cu rv.cu comm.cu euler.cu smooth.cu api.cu; do
+for f in setup.cpp assembly.cu linalg.cu persist.cu rv.cu comm.cu euler.cu smooth.cu api.cu; do
   x=""; [ "$f" = setup.cpp ] && x="-x cu"
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fopenmp,-O3 \
     --expt-relaxed-constexpr "$@" $x -c $src/$f -o $tmp/${f%.*}.o &
