@@ -344,9 +344,21 @@ def main():
     ctx.state_set(uh=u0, u_n=u0, u_old=u0, u_oo=u0, RH=np.zeros(nn), t=0.0)
     ctx.step_scalar(p, W)
     barrier()
+    if world > 1:
+        ctx.comm_timers(reset=True)
     with ClockSampler(local_rank) as clk:
         st = ctx.step_scalar(p, K)
     barrier()
+    # device-measured waits of THIS (un-profiled) run, per step and rank 0: time CTAs spent waiting for halo values,
+    # the cross-rank part of the in-kernel all-reduces, and the barrier time of one worker CTA of the persistent solver
+    comm_wait = None
+    if world > 1:
+        tm = ctx.comm_timers(reset=True)
+        comm_wait = {"halo_wait_us_per_cta_wait": tm["halo_wait_us_total"] / max(tm["halo_waits"], 1),
+                     "halo_waits_per_step": tm["halo_waits"] / K, "halo_wait_us_max": tm["halo_wait_us_max"],
+                     "allreduce_us_per_step": tm["allreduce_us_total"] / K, "allreduces_per_step": tm["allreduces"] / K,
+                     "allreduce_us_max": tm["allreduce_us_max"],
+                     "solver_barrier_us_per_step_worker0": tm["barrier_us_worker0"] / K, "solver_barriers_per_step": tm["barriers"] / K}
     dev_ms = st["device_ms"]
     if dist is not None:
         t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -491,7 +503,7 @@ def main():
                        "layer; data plane = stores into the neighbours' CUDA-IPC mailboxes over NVLink from inside the SpMV-type "
                        "kernels (halo) and tagged-word all-reduce kernels; NCCL only for set-up (handle exchange) and as the "
                        "CFEM_COMM=nccl fallback"),
-                   "comm": ctx.comm_stats() if world > 1 else None, "tiles": ctx.num_tiles,
+                   "comm": ctx.comm_stats() if world > 1 else None, "comm_wait": comm_wait, "tiles": ctx.num_tiles,
                    "l2": "no flush between steps: a step streams 3 matrices (2 x 59 MB values + 21 MB pattern) and ~30 nodal vectors "
                          "(8.4 MB each) = ~400 MB > the 126 MB L2, so every step starts with cold lines; WITHIN a solve the matrix is "
                          "deliberately kept L2-resident (persisting access-policy window)",

@@ -40,6 +40,20 @@ class RV:
         if degree != 1:
             raise NotImplementedError("the GPU path covers P1 (degree=1) only")
 
+    def _check_patches(self, node_patches):
+        """The kernels use the mesh's own P1 graph.  A ``node_patches`` argument that did not come from this
+        context (``SI.get_patch_dictionary``) must describe the same graph -- anything else cannot be honoured
+        and is refused instead of being silently ignored."""
+        if node_patches is None or getattr(node_patches, "ctx", None) is self._ctx:
+            return
+        rowptr, colidx = self._ctx.csr_pattern()
+        if len(node_patches) != self._ctx.n:
+            raise ValueError("node_patches does not belong to this mesh (size mismatch)")
+        rng = np.random.default_rng(0)
+        for i in rng.integers(0, self._ctx.n, size=min(64, self._ctx.n)):
+            if set(int(j) for j in node_patches[int(i)]) != set(colidx[rowptr[i]:rowptr[i + 1]].tolist()):
+                raise ValueError("node_patches differs from the P1 graph of the mesh; custom patches are not supported")
+
     def get_epsilon(self, uh, velocity_field, residual, h, degree=1, flux=None):
         """``RV.py:27-40``: min(Cvel h |f'(u)|, Crv h^2 |R|), pointwise."""
         self._check_degree(degree)
@@ -55,9 +69,10 @@ class RV:
         return NodalFunction(eps, "epsilon")
 
     def get_epsilon_nonlinear(self, uh, u_n, velocity_field, Rh, h_CG, node_patches=None, degree=1, flux=None):
-        """``RV.py:56-90``.  ``node_patches`` is accepted for signature parity; the patches
-        are the mesh's own P1 graph, already resident on the GPU."""
+        """``RV.py:56-90``.  The patches are the mesh's own P1 graph, already resident on the GPU;
+        ``node_patches`` is checked against it (see ``_check_patches``)."""
         self._check_degree(degree)
+        self._check_patches(node_patches)
         eps = self._ctx.rv_epsilon("nonlinear", _identify_flux(velocity_field, flux), self.Cvel, self.Crv,
                                    uh=uh, u_n=u_n, Rh=Rh, h=h_CG)
         return NodalFunction(eps, "epsilon")
@@ -65,6 +80,7 @@ class RV:
     def get_epsilon_linear(self, uh, u_n, velocity_field, Rh, h_CG, node_patches=None, degree=1):
         """``RV.py:92-127``; ``velocity_field`` is the P1 velocity function w."""
         self._check_degree(degree)
+        self._check_patches(node_patches)
         eps = self._ctx.rv_epsilon("linear", L.FLUX_ADVECTION, self.Cvel, self.Crv, uh=uh, u_n=u_n, Rh=Rh,
                                    h=h_CG, w=velocity_field)
         return NodalFunction(eps, "epsilon")

@@ -86,6 +86,7 @@ SIGNATURES = {
     "cfem_num_tiles": (_L, [_P]),
     "cfem_device_bytes": (_L, [_P]),
     "cfem_device_limits": (_I, [_I, _P]),
+    "cfem_comm_timers": (_I, [_P, _P, _I]),
     "cfem_get_csr_pattern": (_I, [_P, _P, _P]),
     "cfem_get_boundary_dofs": (_I, [_P, _P]),
     "cfem_set_dirichlet": (_I, [_P, _P, _L]),
@@ -121,6 +122,9 @@ SIGNATURES = {
     "cfem_host_info": (_L, [_P, _I]),
     "cfem_host_size": (_L, [_P, _I]),
     "cfem_host_copy": (_I, [_P, _I, _P]),
+    "cfem_host_analyse_partitioned": (_I, [_P, _I, _I, _L, _L, _P, _I, _P, _I, _I, _P]),
+    "cfem_host_partition": (_I, [_I, _I, _L, _L, _P, _I, _P, _I, _P]),
+    "cfem_create_partitioned": (_I, [_P, _I, _I, _I, _P, _L, _L, _P, _I, _P, _I, _I, _P]),
     "cfem_host_free": (None, [_P]),
 }
 
@@ -137,10 +141,28 @@ def device_limits(device=0):
     return dict(zip(("l2_bytes", "persisting_l2_max", "access_window_max", "sm_count"), [int(v) for v in out]))
 
 
-def host_analyse(x, cells, order=ORDER_HILBERT, rank=0, world=1):
+PART_HILBERT, PART_METIS = 0, 1
+
+
+def host_partition(x, cells, world, method="metis"):
+    """One part id per node (caller numbering): METIS k-way on the nodal graph, or equal Hilbert ranges."""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    cells = np.ascontiguousarray(cells)
+    ib = 8 if cells.dtype == np.int64 else 4
+    if ib == 4:
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+    part = np.empty(x.shape[0], dtype=np.int32)
+    check(lib.cfem_host_partition(PART_METIS if method == "metis" else PART_HILBERT, int(world), x.shape[0],
+                                  cells.shape[0], ptr(x), x.shape[1], ptr(cells), ib, ptr(part)))
+    return part
+
+
+def host_analyse(x, cells, order=ORDER_HILBERT, rank=0, world=1, node_part=None):
     """Run the once-per-mesh host analysis (no GPU needed) and return its arrays.
 
-    With ``world > 1``: rank's part of the partition (local numbering: owned nodes, then ghosts)."""
+    With ``world > 1``: rank's part of the partition (local numbering: owned nodes, then ghosts);
+    ``node_part``: the caller's partition (``host_partition``), default equal Hilbert ranges."""
     lib = load()
     x = np.ascontiguousarray(x, dtype=np.float64)
     cells = np.ascontiguousarray(cells)
@@ -148,8 +170,9 @@ def host_analyse(x, cells, order=ORDER_HILBERT, rank=0, world=1):
     if ib == 4:
         cells = np.ascontiguousarray(cells, dtype=np.int32)
     h = C.c_void_p()
-    check(lib.cfem_host_analyse_part(C.byref(h), rank, world, x.shape[0], cells.shape[0], ptr(x), x.shape[1],
-                                     ptr(cells), ib, order))
+    node_part = None if node_part is None else np.ascontiguousarray(node_part, dtype=np.int32)
+    check(lib.cfem_host_analyse_partitioned(C.byref(h), rank, world, x.shape[0], cells.shape[0], ptr(x), x.shape[1],
+                                            ptr(cells), ib, order, ptr(node_part)))
     out = {}
     try:
         for name, what in HM_ARRAYS.items():

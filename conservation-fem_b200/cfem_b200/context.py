@@ -38,12 +38,18 @@ class Context:
     (``Code/KPP/KPP_exact.py:85-89``), mass matrices, assembly tiles.
     """
 
-    _cache: "weakref.WeakValueDictionary" = weakref.WeakValueDictionary()
+    # mesh OBJECT -> its context.  Keyed by the object itself (weakly): the entry dies with the mesh, an id() reused
+    # by another object can never alias it, and the context stays alive as long as the mesh does -- a helper called
+    # with nothing but the mesh (get_nodal_h(domain)) builds it once.
+    _cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
-    def __init__(self, domain, device=0, order="hilbert", comm=None):
+    def __init__(self, domain, device=0, order="hilbert", comm=None, partition=None):
         """``comm``: None (one GPU) or ``(rank, world, nccl_id_bytes)`` from ``distributed.make_comm``.
         In a distributed context every rank passes the same global mesh and global-sized fields;
-        results come back at the dofs the rank owns (``distributed.allgather_field`` merges them)."""
+        results come back at the dofs the rank owns (``distributed.allgather_field`` merges them).
+        ``partition``: None = equal ranges of the Hilbert order; ``"metis"`` = METIS k-way on the nodal graph
+        (computed here, identically on every rank); or an int32 array with the owning rank of every node
+        (``distributed.make_partition`` computes it once and broadcasts it)."""
         lib = L.load()
         x, cells = as_mesh(domain)
         self.x = x
@@ -58,8 +64,16 @@ class Context:
         else:
             self.rank, self.world, nid = int(comm[0]), int(comm[1]), comm[2]
             buf = (C.c_char * 128).from_buffer_copy(bytes(nid))
-            L.check(lib.cfem_create_distributed(C.byref(h), int(device), self.rank, self.world, C.addressof(buf),
-                                                x.shape[0], cells.shape[0], L.ptr(x), 2, L.ptr(cells), 4, o))
+            part = None
+            if isinstance(partition, str):
+                part = L.host_partition(x, cells, self.world, partition) if partition != "hilbert" else None
+            elif partition is not None:
+                part = np.ascontiguousarray(partition, dtype=np.int32)
+                if part.size != x.shape[0]:
+                    raise ValueError("partition must hold one rank id per node")
+            self.partition = part
+            L.check(lib.cfem_create_partitioned(C.byref(h), int(device), self.rank, self.world, C.addressof(buf),
+                                                x.shape[0], cells.shape[0], L.ptr(x), 2, L.ptr(cells), 4, o, L.ptr(part)))
         self._h = h
         self._lib = lib
         self.n_owned = lib.cfem_num_owned(h)
@@ -82,14 +96,20 @@ class Context:
 
     @classmethod
     def for_domain(cls, domain, **kw):
-        """One cached context per mesh object (RV / SI / get_nodal_h share it)."""
-        key = id(domain)
-        ctx = cls._cache.get(key)
+        """One cached context per mesh OBJECT (RV / SI / get_nodal_h share it).
+
+        Objects that cannot be weakly referenced or hashed -- plain ``(x, cells)`` tuples, lists -- are not
+        cached: every call builds a context, which the caller should then keep (``Context(domain)``)."""
+        if isinstance(domain, Context):
+            return domain
+        try:
+            ctx = cls._cache.get(domain)
+        except TypeError:          # unhashable / not weak-referenceable
+            return cls(domain, **kw)
         if ctx is None or ctx._h is None:
             ctx = cls(domain, **kw)
             try:
-                cls._cache[key] = ctx
-                ctx._owner = weakref.ref(domain) if not isinstance(domain, (tuple, list)) else None
+                cls._cache[domain] = ctx
             except TypeError:
                 pass
         return ctx
@@ -350,6 +370,14 @@ class Context:
         a, b, d = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         L.check(self._lib.cfem_comm_stats(self._h, C.byref(a), C.byref(b), C.byref(d)))
         return {"halo_exchanges": a.value, "allreduces": b.value, "halo_doubles_sent_per_exchange": d.value}
+
+    def comm_timers(self, reset=True):
+        """Device-measured waits of the peer-memory data plane since the last reset (microseconds / counts)."""
+        out = (C.c_double * 8)()
+        L.check(self._lib.cfem_comm_timers(self._h, out, int(bool(reset))))
+        k = ("halo_wait_us_total", "halo_waits", "halo_wait_us_max", "allreduce_us_total", "allreduces",
+             "allreduce_us_max", "barrier_us_worker0", "barriers")
+        return dict(zip(k, [float(v) for v in out]))
 
     def synchronize(self):
         L.check(self._lib.cfem_synchronize(self._h))

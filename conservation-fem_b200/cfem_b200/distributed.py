@@ -31,6 +31,24 @@ def make_comm(dist=None):
     return (rank, world, bytes(t.cpu().numpy().tobytes()))
 
 
+def make_partition(dist, x, cells, method="metis"):
+    """Owning rank of every node (int32, caller numbering) for ``Context(..., partition=...)``: computed on rank 0
+    (METIS k-way on the nodal graph, or ``"hilbert"`` = equal ranges of the Hilbert order) and broadcast."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return None
+    import torch
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    n = np.asarray(x).shape[0]
+    if rank == 0:
+        part = torch.as_tensor(L.host_partition(x, cells, world, method), device=dev)
+    else:
+        part = torch.empty(n, dtype=torch.int32, device=dev)
+    dist.broadcast(part, src=0)
+    return part.cpu().numpy()
+
+
 def allgather_field(ctx, local_result, dist):
     """Merge per-rank results (valid at owned dofs) into the full field on every rank."""
     if ctx.world == 1:

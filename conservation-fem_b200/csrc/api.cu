@@ -227,7 +227,7 @@ int cfem_device_count(void) {
 
 static int create_impl(cfem_ctx** out, int device, int rank, int world, const void* nccl_id, int64_t n_nodes,
                        int64_t n_cells, const double* x, int xdim, const void* cells, int cell_index_bytes,
-                       int order) {
+                       int order, const int32_t* node_part = nullptr) {
   cfem_ctx* c = nullptr;
   API_BEGIN
   if (!out || !x || !cells) CFEM_THROW(-1, "null argument");
@@ -246,7 +246,7 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   c->sm_count = prop.multiProcessorCount;
   CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   if (world > 1 && !nccl_id) CFEM_THROW(-1, "distributed context needs the NCCL unique id");
-  analyse_mesh(c->hm, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order, rank, world);
+  analyse_mesh(c->hm, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order, rank, world, node_part);
   comm_init(c, rank, world, nccl_id);
   HostMesh& hm = c->hm;
   const int64_t nn = hm.nn;
@@ -380,6 +380,31 @@ int cfem_create_distributed(cfem_ctx** out, int device, int rank, int world, con
   return create_impl(out, device, rank, world, nccl_id128, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order);
 }
 
+int cfem_create_partitioned(cfem_ctx** out, int device, int rank, int world, const void* nccl_id128, int64_t n_nodes,
+                            int64_t n_cells, const double* x, int xdim, const void* cells, int cell_index_bytes,
+                            int order, const int32_t* node_part) {
+  return create_impl(out, device, rank, world, nccl_id128, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order, node_part);
+}
+
+int cfem_host_partition(int method, int world, int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
+                        const void* cells, int cell_index_bytes, int32_t* part_out) {
+  API_BEGIN
+  if (!x || !cells || !part_out) CFEM_THROW(-1, "null argument");
+  if (method == CFEM_PART_METIS) {
+    metis_partition(world, n_nodes, n_cells, cells, cell_index_bytes, part_out);
+  } else if (method == CFEM_PART_HILBERT) {
+    HostMesh hm;   // rank 0's analysis carries the global order and the range offsets
+    analyse_mesh(hm, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, CFEM_ORDER_HILBERT, 0, world);
+    for (int64_t u = 0; u < n_nodes; ++u) {
+      const int64_t g = hm.u2n[u];
+      part_out[u] = (int32_t)(std::upper_bound(hm.part_off.begin(), hm.part_off.end(), g) - hm.part_off.begin()) - 1;
+    }
+  } else {
+    CFEM_THROW(-1, "unknown partition method");
+  }
+  API_END
+}
+
 int64_t cfem_num_owned(const cfem_ctx* c) { return c->dm.no; }
 int64_t cfem_num_ghosts(const cfem_ctx* c) { return c->dm.nn - c->dm.no; }
 int cfem_comm_stats(const cfem_ctx* c, int64_t* halo_exchanges, int64_t* allreduces, int64_t* halo_doubles_sent) {
@@ -387,6 +412,13 @@ int cfem_comm_stats(const cfem_ctx* c, int64_t* halo_exchanges, int64_t* allredu
   if (allreduces) *allreduces = c->allreduces;
   if (halo_doubles_sent) *halo_doubles_sent = (int64_t)c->hm.send_idx.size();
   return 0;
+}
+
+int cfem_comm_timers(cfem_ctx* c, double out[8], int reset) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  comm_timers(c, out, reset != 0);
+  API_END
 }
 
 void cfem_destroy(cfem_ctx* c) {
@@ -1155,6 +1187,19 @@ int cfem_host_analyse_part(cfem_host_mesh** out, int rank, int world, int64_t n_
     if (!out || !x || !cells) CFEM_THROW(-1, "null argument");
     h = new cfem_host_mesh();
     analyse_mesh(h->hm, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order, rank, world);
+    *out = h;
+    return 0;
+  } catch (const cfem::Error& e) { cfem::set_error(e.msg); delete h; return e.code; }
+  catch (const std::exception& e) { cfem::set_error(e.what()); delete h; return -9; }
+}
+int cfem_host_analyse_partitioned(cfem_host_mesh** out, int rank, int world, int64_t n_nodes, int64_t n_cells,
+                                  const double* x, int xdim, const void* cells, int cell_index_bytes, int order,
+                                  const int32_t* node_part) {
+  cfem_host_mesh* h = nullptr;
+  try {
+    if (!out || !x || !cells) CFEM_THROW(-1, "null argument");
+    h = new cfem_host_mesh();
+    analyse_mesh(h->hm, n_nodes, n_cells, x, xdim, cells, cell_index_bytes, order, rank, world, node_part);
     *out = h;
     return 0;
   } catch (const cfem::Error& e) { cfem::set_error(e.msg); delete h; return e.code; }

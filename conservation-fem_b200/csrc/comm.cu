@@ -338,7 +338,9 @@ static void p2p_setup(cfem_ctx* c) {
   cudaFree(dng);
   d.halo_off = kFlagBytes + kRedBytes + kLLBytes;
   d.halo_stride = (((size_t)ng_max * 4 * sizeof(double)) + 255) / 256 * 256 + 256;
-  const size_t bytes = d.halo_off + 2 * d.halo_stride;
+  d.ll_off = d.halo_off + 2 * d.halo_stride;
+  d.ll_stride = (((size_t)ng_max * 2 * sizeof(unsigned long long)) + 255) / 256 * 256 + 256;
+  const size_t bytes = d.ll_off + 2 * d.ll_stride;
   void* box = nullptr;
   CUDA_OK(cudaMalloc(&box, bytes));
   CUDA_OK(cudaMemset(box, 0, bytes));
@@ -408,6 +410,9 @@ static void p2p_setup(cfem_ctx* c) {
   CUDA_OK(cudaMalloc((void**)&d.counter, 2 * sizeof(unsigned int)));
   CUDA_OK(cudaMemset(d.counter, 0, 2 * sizeof(unsigned int)));
   c->allocs.push_back(d.counter);
+  CUDA_OK(cudaMalloc((void**)&d.tim, 8 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMemset(d.tim, 0, 8 * sizeof(unsigned long long)));
+  c->allocs.push_back(d.tim);
   CUDA_OK(cudaMallocHost((void**)&pp->h_error, sizeof(int)));
   *pp->h_error = 0;
   d.error = pp->h_error;
@@ -522,6 +527,9 @@ GhostSrc halo_push(cfem_ctx* c, double* v, bool gated, bool in_consumer) {
     LAUNCHED(c);
   } else {
     g.pushdev = pp->d_dev;
+    // low-latency words instead of values + fence + flag (CFEM_HALO_LL=0: the flag protocol)
+    static const bool ll = !(getenv("CFEM_HALO_LL") && std::string(getenv("CFEM_HALO_LL")) == "0");
+    if (ll) g.ll = (const unsigned long long*)(pp->d.local + pp->d.ll_off + (seq & 1) * pp->d.ll_stride);
   }
   c->halo_exchanges++;
   g.mbox = (const double*)(pp->d.local + pp->d.halo_off + (seq & 1) * pp->d.halo_stride);
@@ -530,6 +538,7 @@ GhostSrc halo_push(cfem_ctx* c, double* v, bool gated, bool in_consumer) {
   g.npeer = npeer;
   g.peer_rank = pp->d_peer_rank;
   g.error = pp->d.error;
+  g.tim = pp->d.tim;
   return g;
 }
 
@@ -577,20 +586,21 @@ int allreduce_partials(cfem_ctx* c, int nslots, double* const* slots, const int*
 
 void persist_comm_args(cfem_ctx* c, const P2PDev** dev, const char** mailbox, size_t* halo_off, size_t* halo_stride,
                        const int32_t** peer_rank, int* npeer, int** error, unsigned long long* halo_seq,
-                       unsigned long long* red_seq) {
+                       unsigned long long* red_seq, unsigned long long** tim) {
   *dev = nullptr; *mailbox = nullptr; *halo_off = 0; *halo_stride = 0; *peer_rank = nullptr; *npeer = 0; *error = nullptr;
-  *halo_seq = 0; *red_seq = 0;
+  *halo_seq = 0; *red_seq = 0; *tim = nullptr;
   if (c->world == 1 || !c->p2p) return;
   P2P* pp = (P2P*)c->p2p;
   *dev = pp->d_dev;
   *mailbox = pp->d.local;
-  *halo_off = pp->d.halo_off;
-  *halo_stride = pp->d.halo_stride;
+  *halo_off = pp->d.ll_off;       // the persistent kernels use the low-latency halo words only
+  *halo_stride = pp->d.ll_stride;
   *peer_rank = pp->d_peer_rank;
   *npeer = pp->d.npeer;
   *error = pp->d.error;
   *halo_seq = pp->halo_seq;
   *red_seq = pp->red_seq;
+  *tim = pp->d.tim;
 }
 
 void persist_comm_advance(cfem_ctx* c, int64_t halo_exchanges, int64_t allreduces) {
@@ -600,6 +610,21 @@ void persist_comm_advance(cfem_ctx* c, int64_t halo_exchanges, int64_t allreduce
   pp->red_seq += (unsigned long long)allreduces;
   c->halo_exchanges += halo_exchanges;
   c->allreduces += allreduces;
+}
+
+// cycles -> microseconds with the device's nominal SM clock; reset: start a new accounting interval
+void comm_timers(cfem_ctx* c, double* out8, bool reset) {
+  for (int k = 0; k < 8; ++k) out8[k] = 0.0;
+  if (c->world == 1 || !c->p2p) return;
+  P2P* pp = (P2P*)c->p2p;
+  unsigned long long h[8];
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaMemcpy(h, pp->d.tim, sizeof(h), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_OK(cudaMemset(pp->d.tim, 0, sizeof(h)));
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+  const double us = khz > 0 ? 1e3 / (double)khz : 0.0;
+  for (int k = 0; k < 8; ++k) out8[k] = (k == 1 || k == 4 || k == 7) ? (double)h[k] : (double)h[k] * us;
 }
 
 bool fin_available(const cfem_ctx* c) { return c->world == 1 || c->p2p != nullptr; }

@@ -72,8 +72,13 @@ struct HostMesh {
   int max_row = 0, max_tile_cells = 0, max_tile_nnz = 0;
 };
 
+// node_part (nullable): caller-numbered part id per node (e.g. from cfem_host_partition); null = equal ranges of the
+// Hilbert order
 void analyse_mesh(HostMesh& hm, int64_t nn, int64_t nc, const double* x, int xdim,
-                  const void* cells, int idx_bytes, int order, int rank = 0, int world = 1);
+                  const void* cells, int idx_bytes, int order, int rank = 0, int world = 1,
+                  const int32_t* node_part = nullptr);
+// METIS k-way partition of the nodal graph (partition.cpp): one part id per caller node
+void metis_partition(int world, int64_t nn, int64_t nc, const void* cells, int idx_bytes, int32_t* part_out);
 // user dof -> local id (owned or ghost) or -1 if this rank does not hold it
 int32_t user_to_local(const HostMesh& hm, int64_t user_dof);
 

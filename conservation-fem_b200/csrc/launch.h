@@ -92,13 +92,17 @@ bool bicgstab_persist_available(cfem_ctx* c);
 void launch_bicg_persist(cfem_ctx* c, const Matrix& A, const double* rhat, double* x, double* r, double* p, double* v,
                          double* t, double rtol2, double atol2, int max_it);
 void persist_plan_free(cfem_ctx* c);
+bool cheb_persist_available(cfem_ctx* c);
+void launch_cheb_persist(cfem_ctx* c, const Matrix& A, const double* b, double* x_in, double* x_other, double* d,
+                         bool first, int iters, double rho0, double sigma1, double theta, double delta);
 struct P2PDev;
 // exchange tables / current sequence numbers for a kernel that runs several exchanges by itself, and the bump of the
 // host-side sequence counters once the number of iterations it ran is known (comm.cu; no-ops on one GPU)
 void persist_comm_args(cfem_ctx* c, const P2PDev** dev, const char** mailbox, size_t* halo_off, size_t* halo_stride,
                        const int32_t** peer_rank, int* npeer, int** error, unsigned long long* halo_seq,
-                       unsigned long long* red_seq);
+                       unsigned long long* red_seq, unsigned long long** tim);
 void persist_comm_advance(cfem_ctx* c, int64_t halo_exchanges, int64_t allreduces);
+void comm_timers(cfem_ctx* c, double* out8, bool reset);
 
 // ---- RV (rv.cu) ------------------------------------------------------------------
 // sum / min / max of v -> c->scalars[0..2] (device), no host sync

@@ -160,7 +160,24 @@ double norm2(cfem_ctx* c, const double* v, int64_t n) {
 // ---------------------------------------------------------------- SpMV
 // ghost entries of the input vector come from the mailbox when the exchange was push-only
 // (a select on the base pointer, then ONE load: predicated twin loads cost ~30% of the kernel)
-#define XG(vec, col) ((GHOST ? (((col) >= no) ? mbox_shifted : (vec)) : (vec))[col])
+#define XG(vec, col) ((GHOST && (col) >= no) ? ghost_value(gsrc, mbox_shifted, (col), no) : (vec)[col])
+// (not inlined: a handful of ghost entries per boundary tile take this path, and the polling loop inlined into the
+// staging code cost the distributed kernel variants 32 bytes of spills in their hot loop)
+__device__ __noinline__ double ghost_value_ll(const unsigned long long* ll2, const unsigned int tag, int* error) {
+  return ll_load(ll2, tag, error);
+}
+__device__ __forceinline__ double ghost_value(const GhostSrc& g, const double* mbox_shifted, const int col, const int64_t no) {
+  if (g.ll) return ghost_value_ll(g.ll + 2 * (size_t)(col - no), (unsigned int)g.seq, g.error);
+  return mbox_shifted[col];
+}
+// producer half of the fused halo exchange, run by CTA 0 of a SpMV-type kernel
+__device__ __forceinline__ void ghost_push(const GhostSrc& g, const double* __restrict__ v, const bool gate) {
+  if (g.ll) {
+    if (!gate) push_ll(g.pushdev, g.seq, [v](int node) { return v[node]; });
+  } else {
+    push_cta(g.pushdev, v, g.seq, gate);
+  }
+}
 
 // CSR-stream SpMV: a CTA takes one assembly tile (<= kTileNodes consecutive rows,
 // <= kTileNnzCap entries).  Every thread streams entries p, p+256, ... of the
@@ -180,7 +197,7 @@ k_spmv_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
   // previous kernel's drain; x, status, the mailbox and the partials are touched after it.
   int bid = blockIdx.x, nblk = gridDim.x;
   if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
-    if (bid == 0) { pdl_wait(); pdl_launch(); push_cta(gsrc.pushdev, x, gsrc.seq, status && status[0]); return; }
+    if (bid == 0) { pdl_wait(); pdl_launch(); ghost_push(gsrc, x, status && status[0]); return; }
     --bid; --nblk;
   }
   __shared__ double prod[kTileNnzCap];
@@ -202,7 +219,7 @@ k_spmv_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
       synced = true;
       if (status && status[0]) return;
     }
-    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
+    if (GHOST && t >= n_interior && !waited) { if (!gsrc.ll) ghost_wait(gsrc); waited = true; }
     const int start = rp[0], cnt = rp[nrows] - start;
     const double* __restrict__ v = vals + start;
     const int32_t* __restrict__ ci = colidx + start;
@@ -348,7 +365,7 @@ k_tile_t16(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ ti
            const int32_t* __restrict__ status, const Fin fin) {
   int bid = blockIdx.x, nblk = gridDim.x;
   if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
-    if (bid == 0) { pdl_wait(); pdl_launch(); push_cta(gsrc.pushdev, x, gsrc.seq, status && status[0]); return; }
+    if (bid == 0) { pdl_wait(); pdl_launch(); ghost_push(gsrc, x, status && status[0]); return; }
     --bid; --nblk;
   }
   extern __shared__ double t16_smem[];
@@ -364,7 +381,14 @@ k_tile_t16(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ ti
   bool waited = false, synced = false;
   const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;  // mbox_shifted[col] == mailbox[col - no]
   if (bid >= ntiles) { pdl_wait(); pdl_launch(); }
-  for (int t = bid; t < ntiles; t += nblk) {
+  // GHOST: the last round of tile_order holds the tiles with ghost columns; it is visited in the middle so the halo
+  // values pushed at the start of the kernel have arrived and any remaining wait is followed by more work
+  const int nrounds = (ntiles + nblk - 1) / nblk;
+  const int mid = nrounds / 2;
+  for (int kk = 0; kk < nrounds; ++kk) {
+    const int k = (!GHOST || nrounds < 3) ? kk : (kk == mid ? nrounds - 1 : (kk > mid ? kk - 1 : kk));
+    const int t = bid + k * nblk;
+    if (t >= ntiles) continue;
     const int tile = GHOST ? tile_order[t] : t;
     const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
     const int e0 = extptr[tile], ne = extptr[tile + 1] - e0;
@@ -391,7 +415,7 @@ k_tile_t16(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ ti
     if (tid + kTileNodes < cnt) v1 = v[tid + kTileNodes];
     if (tid + 2 * kTileNodes < cnt) v2 = v[tid + 2 * kTileNodes];
     if (tid + 3 * kTileNodes < cnt) v3 = v[tid + 3 * kTileNodes];
-    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
+    if (GHOST && t >= n_interior && !waited) { if (!gsrc.ll) ghost_wait(gsrc); waited = true; }
     // ---- stage x: own rows, then the external columns
     double xown = 0.0;
     if (tid < nrows) { xown = x[n0 + tid]; xs[tid] = xown; }
@@ -545,7 +569,7 @@ k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
               double* __restrict__ part_bb) {
   int bid = blockIdx.x, nblk = gridDim.x;
   if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
-    if (bid == 0) { pdl_wait(); pdl_launch(); push_cta(gsrc.pushdev, xk, gsrc.seq, false); return; }
+    if (bid == 0) { pdl_wait(); pdl_launch(); ghost_push(gsrc, xk, false); return; }
     --bid; --nblk;
   }
   __shared__ double prod[kTileNnzCap];
@@ -562,7 +586,7 @@ k_cheb_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
     for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i];
     __syncthreads();
     if (!synced) { pdl_wait(); pdl_launch(); synced = true; }   // mesh tables only above (see k_spmv_stream)
-    if (GHOST && t >= n_interior && !waited) { ghost_wait(gsrc); waited = true; }
+    if (GHOST && t >= n_interior && !waited) { if (!gsrc.ll) ghost_wait(gsrc); waited = true; }
     const int start = rp[0], cnt = rp[nrows] - start;
     const double* __restrict__ v = vals + start;
     const int32_t* __restrict__ ci = colidx + start;
@@ -630,7 +654,25 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
   int target = predict ? *predict : 28;
   if (target < 2) target = 2;
   if (target > max_it) target = max_it;
+  const bool persist = use_t16() && cheb_persist_available(c);
   while (true) {
+    if (persist) {
+      // all iterations up to the next check in ONE cooperative launch (persist.cu); the scope stands for
+      // (target - it) iterations so the breakdown keeps reporting time per iteration
+      const int n_it = target - it;
+      {
+        ProfScope chain(c, PROF_CHEB, n_it);
+        launch_cheb_persist(c, A, b, xa, xb, d, it == 0, n_it, rho, sigma1, theta, delta);
+      }
+      for (int k = 0; k < n_it; ++k)
+        if (it + k > 0) rho = 1.0 / (2.0 * sigma1 - rho);
+      if (n_it & 1) std::swap(xa, xb);
+      it = target;
+      CUDA_OK(cudaMemcpyAsync(c->h_status, c->status, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + S_RELRES, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_OK(cudaStreamSynchronize(c->stream));
+      if (c->h_status[3]) CFEM_THROW(-5, "a grid barrier of the persistent Chebyshev solver timed out");
+    } else {
     // the iterations up to the next check are timed as ONE scope of (target - it) launches: the per-launch
     // figure then is the in-situ one (back-to-back launches, programmatic dependent launch active)
     {
@@ -669,6 +711,7 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
     { ProfScope ps(c, PROF_KRYLOV_VEC); launch_pdl(k_relres, 1, kBlock, 0, c->stream, part, np_rr, np_bb, c->scalars); LAUNCHED(c); }
     CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + S_RELRES, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
     res.iters = it;
     res.relres = c->h_pinned[0];
     if (!(res.relres == res.relres)) break;

@@ -17,10 +17,15 @@ struct P2PDev {  // passed to kernels by value
   int32_t peer_rank[kMaxWorld];
   int npeer, world, rank;
   size_t halo_off, halo_stride;  // bytes
+  size_t ll_off, ll_stride;      // low-latency halo area: two generations of two 64-bit words per ghost value
   const int32_t *send_ptr, *send_idx;
   unsigned int* counter;         // 2 block counters
   int* error;                    // pinned host flag
   int64_t n_owned, n_ghost;
+  // wait accounting (SM cycles), always on: [0] sum [1] count [2] max of ghost_wait per waiting CTA;
+  // [3] sum [4] count [5] max of the cross-rank part of an in-kernel all-reduce; [6] sum [7] count of the time the
+  // first worker CTA of the persistent solver spends in grid barriers (local wait + reduction + all-reduce)
+  unsigned long long* tim;
 };
 
 // Where a SpMV-type kernel finds the ghost entries of its input vector.
@@ -38,6 +43,11 @@ struct GhostSrc {
   // boundary values into the neighbours' mailboxes (and publishes seq) while the other CTAs already
   // work on interior tiles; the kernel is then launched with one extra CTA.
   const P2PDev* pushdev = nullptr;      // device copy of the exchange tables
+  unsigned long long* tim = nullptr;    // wait accounting, see P2PDev::tim
+  // Low-latency halo (default for the fused push): ghost value g of this exchange sits in ll[2g], ll[2g+1] as two
+  // self-validating words {32 data bits | 32-bit sequence tag}; the reader polls the words it needs, nobody waits for
+  // a flag and the producer needs no system-scope fence (see ll_store / ll_load).
+  const unsigned long long* ll = nullptr;
 };
 
 __device__ __forceinline__ bool wait_flag(const volatile unsigned long long* f, unsigned long long seq, int* error) {
@@ -46,6 +56,43 @@ __device__ __forceinline__ bool wait_flag(const volatile unsigned long long* f, 
     if (clock64() - t0 > 60000000000LL) { *error = 1; return false; }
   }
   return true;
+}
+
+// ---- low-latency halo words ------------------------------------------------------------------------------------------
+// A double travels as two aligned 8-byte words, each carrying 32 of its bits and the 32-bit sequence tag of the
+// exchange.  An aligned 8-byte store is delivered atomically, so a word whose tag matches is complete: the tag is the
+// arrival flag.  Compared with values + __threadfence_system + flag this takes one NVLink store latency (~2 us)
+// instead of ~9 us from the producer's first load to the consumer's first use.  Tags start at 1; the area is zeroed.
+__device__ __forceinline__ void ll_store(unsigned long long* dst2, const double v, const unsigned int tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  ((volatile unsigned long long*)dst2)[0] = (bits & 0xffffffff00000000ull) | tag;
+  ((volatile unsigned long long*)dst2)[1] = (bits << 32) | tag;
+}
+__device__ __forceinline__ double ll_load(const unsigned long long* src2, const unsigned int tag, int* error) {
+  const volatile unsigned long long* s = (const volatile unsigned long long*)src2;
+  unsigned long long hi = s[0], lo = s[1];
+  if ((unsigned int)hi != tag || (unsigned int)lo != tag) {
+    const long long t0 = clock64();
+    do {
+      if (clock64() - t0 > 40000000000LL) { if (error) *error = 1; break; }
+      hi = s[0]; lo = s[1];
+    } while ((unsigned int)hi != tag || (unsigned int)lo != tag);
+  }
+  return __longlong_as_double((long long)((hi & 0xffffffff00000000ull) | (lo >> 32)));
+}
+
+// low-latency producer half, run by ONE CTA: f(node) for every owned boundary node -> the neighbours' LL areas
+template <class F>
+__device__ __forceinline__ void push_ll(const P2PDev* __restrict__ a, const unsigned long long seq, const F f) {
+  const int npeer = a->npeer;
+  const size_t gen = a->ll_off + (size_t)(seq & 1) * a->ll_stride;
+  const unsigned int tag = (unsigned int)seq;
+  for (int k = 0; k < npeer; ++k) {
+    const int s0 = a->send_ptr[k], cnt = a->send_ptr[k + 1] - s0;
+    unsigned long long* dst = (unsigned long long*)(a->peer_base[k] + gen) + 2 * (size_t)a->dst_off[k];
+    const int32_t* __restrict__ idx = a->send_idx + s0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) ll_store(dst + 2 * (size_t)i, f(idx[i]), tag);
+  }
 }
 
 // The whole producer half of a halo exchange, run by ONE CTA: owned boundary values of v -> the
@@ -70,10 +117,18 @@ __device__ __forceinline__ void push_cta(const P2PDev* __restrict__ a, const dou
 
 // called by all threads of a CTA before it touches a boundary tile
 __device__ __forceinline__ void ghost_wait(const GhostSrc& g) {
-  if ((int)threadIdx.x < g.npeer)
+  const long long t0 = clock64();
+  if ((int)threadIdx.x < g.npeer) {
     wait_flag((const volatile unsigned long long*)(g.flags + 8 * g.peer_rank[threadIdx.x]), g.seq, g.error);
+    __threadfence_system();   // by the observing threads only; the barrier below extends the order to the CTA
+  }                           // (a system-scope fence in all 256 threads cost ~4 us per wait)
   __syncthreads();
-  __threadfence_system();
+  if (g.tim && threadIdx.x == 0) {
+    const unsigned long long dt = (unsigned long long)(clock64() - t0);
+    atomicAdd(g.tim + 0, dt);
+    atomicAdd(g.tim + 1, 1ull);
+    atomicMax(g.tim + 2, dt);
+  }
 }
 
 // ---- in-kernel finalisation of reductions -------------------------------------------------------------------------
@@ -94,6 +149,7 @@ struct Slots { double* p[NS]; };
 template <int NS>
 __device__ __forceinline__ void cta_allreduce(const P2PDev* __restrict__ a, const unsigned long long seq, double* sums) {
   __shared__ double recv[NS][kMaxWorld];
+  const long long t_in = clock64();
   const int world = a->world, rank = a->rank;
   const int parity = (int)(seq & 1);
   const unsigned int tag = (unsigned int)seq;
@@ -122,6 +178,12 @@ __device__ __forceinline__ void cta_allreduce(const P2PDev* __restrict__ a, cons
     sums[threadIdx.x] = r;
   }
   __syncthreads();
+  if (a->tim && threadIdx.x == 0) {
+    const unsigned long long dt = (unsigned long long)(clock64() - t_in);
+    atomicAdd(a->tim + 3, dt);
+    atomicAdd(a->tim + 4, 1ull);
+    atomicMax(a->tim + 5, dt);
+  }
 }
 
 // Every thread of every participating CTA calls this after thread 0 of the CTA has stored part.p[k][cta].

@@ -37,7 +37,7 @@ namespace cfem {
 
 // device scalars / partial slots shared with linalg.cu
 enum { PS_BB = 3, PS_RELRES = 7, PS_RR = 8, PS_D0 = 16, PS_RHO0 = 21 };
-enum { PP_PQ = 0, PP_RR = 3, PP_A = 5 };
+enum { PP_PQ = 0, PP_RR = 3, PP_BB = 4, PP_A = 5 };
 
 struct BicgArgs {
   int64_t no;
@@ -54,11 +54,12 @@ struct BicgArgs {
   // distributed (dev == nullptr on one GPU)
   const P2PDev* dev;
   const char* mailbox;      // local mailbox base
-  size_t halo_off, halo_stride;
+  size_t halo_off, halo_stride;   // of the low-latency halo area (P2PDev::ll_off / ll_stride)
   const int32_t* peer_rank;
   int npeer;
   int* error;
   unsigned long long halo_seq0, red_seq0;
+  unsigned long long* tim;  // wait accounting (P2PDev::tim), null on one GPU
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -74,6 +75,7 @@ __device__ __forceinline__ void grid_reduce(const BicgArgs& a, const int nblk, c
                                             const unsigned long long rseq, double* out, double* sums, unsigned int& gen) {
   __shared__ bool s_last;
   ++gen;
+  const long long t_in = clock64();
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -132,22 +134,21 @@ __device__ __forceinline__ void grid_reduce(const BicgArgs& a, const int nblk, c
     if ((int)threadIdx.x < NS) sums[threadIdx.x] = __ldcg(out + threadIdx.x);
   }
   __syncthreads();
+  if (a.tim && threadIdx.x == 0 && blockIdx.x == 1) {   // first worker CTA of a distributed run
+    atomicAdd(a.tim + 6, (unsigned long long)(clock64() - t_in));
+    atomicAdd(a.tim + 7, 1ull);
+  }
 }
 
-// owned boundary values f(node) -> the neighbours' mailboxes (generation seq & 1), then the sequence number
-template <class F>
-__device__ __forceinline__ void push_values(const P2PDev* __restrict__ a, const unsigned long long seq, const F f) {
-  const int npeer = a->npeer;
-  const size_t gen = a->halo_off + (size_t)(seq & 1) * a->halo_stride;
-  for (int k = 0; k < npeer; ++k) {
-    const int s0 = a->send_ptr[k], cnt = a->send_ptr[k + 1] - s0;
-    double* dst = (double*)(a->peer_base[k] + gen) + a->dst_off[k];
-    const int32_t* __restrict__ idx = a->send_idx + s0;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = f(idx[i]);
-  }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < npeer) *(volatile unsigned long long*)(a->peer_base[threadIdx.x] + 8 * a->rank) = seq;
+// Order in which a CTA visits its rounds (round k = tile wid + k * nwork of tile_order).  tile_order keeps the tiles
+// with ghost columns at the end, i.e. in the last round; visiting that round in the MIDDLE gives the neighbours'
+// halo values (pushed at the start of the phase) time to arrive, and whatever wait remains is followed by more work
+// of the same CTA instead of falling on the barrier.  One GPU: plain order.
+template <bool GHOST>
+__device__ __forceinline__ int round_of(const int kk, const int nrounds) {
+  if (!GHOST || nrounds < 3) return kk;
+  const int mid = nrounds / 2;
+  return kk == mid ? nrounds - 1 : (kk > mid ? kk - 1 : kk);
 }
 
 // One SpMV-type phase over this CTA's tiles.  MODE 0: x = p, y = v, acc[0] += rhat.y.  MODE 1: x = r - alpha v,
@@ -158,10 +159,14 @@ __device__ __forceinline__ void spmv_phase(const BicgArgs& a, const int wid, con
                                            double* acc) {
   const int tid = threadIdx.x;
   const int64_t no = a.no;
-  const double* const mbox_shifted =
-      GHOST ? (const double*)(a.mailbox + a.halo_off + (size_t)(hseq & 1) * a.halo_stride) - no : nullptr;
-  bool waited = false;
-  for (int t = wid; t < a.ntiles; t += nwork) {
+  // low-latency halo words of this exchange (p2p.cuh): ghost g in ll[2g], ll[2g+1], polled by the reader
+  const unsigned long long* const ll =
+      GHOST ? (const unsigned long long*)(a.mailbox + a.halo_off + (size_t)(hseq & 1) * a.halo_stride) : nullptr;
+  const unsigned int tag = (unsigned int)hseq;
+  const int nrounds = (a.ntiles + nwork - 1) / nwork;
+  for (int kk = 0; kk < nrounds; ++kk) {
+    const int t = wid + round_of<GHOST>(kk, nrounds) * nwork;
+    if (t >= a.ntiles) continue;
     const int tile = GHOST ? a.tile_order[t] : t;
     const int n0 = a.tile_node[tile], nrows = a.tile_node[tile + 1] - n0;
     const int e0 = a.tile_extptr[tile], ne = a.tile_extptr[tile + 1] - e0;
@@ -175,12 +180,6 @@ __device__ __forceinline__ void spmv_phase(const BicgArgs& a, const int wid, con
     if (tid + kTileNodes < cnt) { v1 = v[tid + kTileNodes]; l1 = lc[tid + kTileNodes]; }
     if (tid + 2 * kTileNodes < cnt) { v2 = v[tid + 2 * kTileNodes]; l2 = lc[tid + 2 * kTileNodes]; }
     if (tid + 3 * kTileNodes < cnt) { v3 = v[tid + 3 * kTileNodes]; l3 = lc[tid + 3 * kTileNodes]; }
-    if (GHOST && t >= a.n_interior && !waited) {
-      GhostSrc g;
-      g.flags = a.mailbox; g.seq = hseq; g.peer_rank = a.peer_rank; g.npeer = a.npeer; g.error = a.error;
-      ghost_wait(g);
-      waited = true;
-    }
     // ---- stage x: own rows, then the external columns (other CTAs' rows: L2 loads, see the file header)
     double xown = 0.0, rh = 0.0, di = 0.0;
     if (tid < nrows) {
@@ -193,8 +192,18 @@ __device__ __forceinline__ void spmv_phase(const BicgArgs& a, const int wid, con
     for (int e = tid; e < ne; e += kTileNodes) {
       const int cc = a.tile_ext[e0 + e];
       double val;
-      if (GHOST && cc >= no) val = mbox_shifted[cc];
-      else val = MODE == 0 ? __ldcg(a.p + cc) : __ldcg(a.r + cc) - alpha * __ldcg(a.v + cc);
+      if (GHOST && cc >= no) {
+        const long long t0 = clock64();
+        val = ll_load(ll + 2 * (size_t)(cc - no), tag, a.error);
+        if (a.tim) {
+          const unsigned long long dt = (unsigned long long)(clock64() - t0);
+          atomicAdd(a.tim + 0, dt);
+          atomicAdd(a.tim + 1, 1ull);
+          atomicMax(a.tim + 2, dt);
+        }
+      } else {
+        val = MODE == 0 ? __ldcg(a.p + cc) : __ldcg(a.r + cc) - alpha * __ldcg(a.v + cc);
+      }
       xs[kTileNodes + e] = val;
     }
     __syncthreads();
@@ -254,7 +263,7 @@ k_bicg_persist(const BicgArgs a) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     if (comm_cta) {
       const double* p = a.p;
-      push_values(a.dev, hseq, [p](int node) { return __ldcg(p + node); });
+      if (a.dev) push_ll(a.dev, hseq, [p](int node) { return __ldcg(p + node); });
     } else {
       spmv_phase<0, GHOST>(a, wid, nwork, 0.0, hseq, prod, xs, rp, acc);
       const double s0 = block_sum(acc[0], red);
@@ -271,7 +280,7 @@ k_bicg_persist(const BicgArgs a) {
     ++hseq;
     if (comm_cta) {
       const double *r = a.r, *v = a.v;
-      push_values(a.dev, hseq, [r, v, alpha](int node) { return __ldcg(r + node) - alpha * __ldcg(v + node); });
+      if (a.dev) push_ll(a.dev, hseq, [r, v, alpha](int node) { return __ldcg(r + node) - alpha * __ldcg(v + node); });
     } else {
       acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
       spmv_phase<1, GHOST>(a, wid, nwork, alpha, hseq, prod, xs, rp, acc);
@@ -334,37 +343,219 @@ k_bicg_persist(const BicgArgs a) {
   }
 }
 
-// ---- host side ------------------------------------------------------------------------------------------------
-struct PersistPlan { int grid = 0; size_t smem = 0; bool ok = false, tried = false; };
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent Chebyshev mass solve: all iterations of  r = b - M x, z = D^-1 r, d = c1 d + c2 z, x+ = x + d  in one
+// cooperative launch (x ping-pongs between two buffers; a plain grid barrier separates the iterations; the
+// row-equilibrated norms ||D^-1 r||, ||D^-1 b|| are reduced once, at the end).  Replaces the LU solve of the residual
+// projection (Code/KPP/KPP_exact.py:128-137, Code/Utils/helpers.py:35).  In a distributed context the iterations of
+// neighbouring ranks are coupled only through the halo flags (no global synchronisation).
+struct ChebArgs {
+  int64_t no;
+  int ntiles, n_interior, ext_cap;
+  const int32_t *tile_order, *tile_node, *rowptr, *tile_extptr, *tile_ext;
+  const uint16_t* lc16;
+  const double *vals, *dinv, *b;
+  double *x0, *x1, *d;      // iteration k reads (k & 1 ? x1 : x0) and writes the other one
+  double *part, *scalars;
+  int32_t* status;
+  unsigned int* bar;
+  int first;                // this launch starts the solve (d undefined, ||D^-1 b|| wanted)
+  int iters;                // iterations in this launch
+  double rho0, sigma1, theta, delta;   // recurrence state at entry
+  const P2PDev* dev;
+  const char* mailbox;
+  size_t halo_off, halo_stride;
+  const int32_t* peer_rank;
+  int npeer;
+  int* error;
+  unsigned long long halo_seq0, red_seq0;
+  unsigned long long* tim;
+};
 
-template <bool GHOST>
-static bool plan_one(cfem_ctx* c, PersistPlan& pl) {
-  pl.smem = sizeof(double) * ((size_t)kTileNnzCap + kTileNodes + c->dm.ext_cap);
-  if (cudaFuncSetAttribute(k_bicg_persist<GHOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) { cudaGetLastError(); return false; }
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bicg_persist<GHOST>, kTileNodes, pl.smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return false; }
-  int coop = 0;
-  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
-  if (!coop) return false;
-  int64_t grid = (int64_t)occ * c->sm_count;
-  const int64_t want = c->dm.ntiles + (GHOST ? 1 : 0);
-  if (grid > want) grid = want;
-  if (grid > kMaxPartials) grid = kMaxPartials;
-  if (grid < (GHOST ? 2 : 1)) return false;
-  pl.grid = (int)grid;
-  return true;
+__device__ __forceinline__ void grid_sync(unsigned int* bar, int32_t* status, int* error, const int nblk, unsigned int& gen) {
+  ++gen;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(bar, 1u);
+    if (t == (unsigned int)nblk - 1u) {
+      bar[0] = 0;
+      __threadfence();
+      atomicExch(bar + 1, gen);
+    } else {
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_u32(bar + 1) - gen) < 0) {
+        if (clock64() - t0 > 20000000000LL || *(volatile int32_t*)(status + 3)) {
+          status[3] = 1;
+          if (error) *error = 1;
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
 }
 
-bool bicgstab_persist_available(cfem_ctx* c) {
-  static const bool off = getenv("CFEM_BICGSTAB") && std::string(getenv("CFEM_BICGSTAB")) != "persist";
-  if (off) return false;
+template <bool GHOST>
+__global__ void __launch_bounds__(kTileNodes, CFEM_PERSIST_MINB)
+k_cheb_persist(const ChebArgs a) {
+  extern __shared__ double ps_smem[];
+  double* const prod = ps_smem;
+  double* const xs = ps_smem + kTileNnzCap;
+  __shared__ int32_t rp[kTileNodes + 1];
+  __shared__ double red[9];
+  __shared__ double sums[2];
+  const int tid = threadIdx.x;
+  const int nblk = gridDim.x;
+  const bool comm_cta = GHOST && blockIdx.x == 0;
+  const int nwork = GHOST ? nblk - 1 : nblk;
+  const int wid = GHOST ? (int)blockIdx.x - 1 : (int)blockIdx.x;
+  const int64_t no = a.no;
+  unsigned int gen = 0;
+  unsigned long long hseq = a.halo_seq0;
+  double rho = a.rho0;
+  double zz = 0.0, bb = 0.0;
+  for (int it = 0; it < a.iters; ++it) {
+    const bool first = a.first && it == 0, last = it == a.iters - 1;
+    const double* __restrict__ xin = (it & 1) ? a.x1 : a.x0;
+    double* __restrict__ xout = (it & 1) ? a.x0 : a.x1;
+    double c1 = 0.0, c2 = 1.0 / a.theta;
+    if (!first) {
+      const double rho_new = 1.0 / (2.0 * a.sigma1 - rho);
+      c1 = rho_new * rho;
+      c2 = 2.0 * rho_new / a.delta;
+      rho = rho_new;
+    }
+    ++hseq;
+    if (comm_cta) {
+      if (a.dev) push_ll(a.dev, hseq, [xin](int node) { return __ldcg(xin + node); });
+    } else {
+      const unsigned long long* const ll =
+          GHOST ? (const unsigned long long*)(a.mailbox + a.halo_off + (size_t)(hseq & 1) * a.halo_stride) : nullptr;
+      const unsigned int tag = (unsigned int)hseq;
+      const int nrounds = (a.ntiles + nwork - 1) / nwork;
+      for (int kk = 0; kk < nrounds; ++kk) {
+        const int t = wid + round_of<GHOST>(kk, nrounds) * nwork;
+        if (t >= a.ntiles) continue;
+        const int tile = GHOST ? a.tile_order[t] : t;
+        const int n0 = a.tile_node[tile], nrows = a.tile_node[tile + 1] - n0;
+        const int e0 = a.tile_extptr[tile], ne = a.tile_extptr[tile + 1] - e0;
+        const int start = a.rowptr[n0], cnt = a.rowptr[n0 + nrows] - start;
+        for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = a.rowptr[n0 + i] - start;
+        const double* __restrict__ v = a.vals + start;
+        const uint16_t* __restrict__ lc = a.lc16 + start;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+        if (tid < cnt) { v0 = v[tid]; l0 = lc[tid]; }
+        if (tid + kTileNodes < cnt) { v1 = v[tid + kTileNodes]; l1 = lc[tid + kTileNodes]; }
+        if (tid + 2 * kTileNodes < cnt) { v2 = v[tid + 2 * kTileNodes]; l2 = lc[tid + 2 * kTileNodes]; }
+        if (tid + 3 * kTileNodes < cnt) { v3 = v[tid + 3 * kTileNodes]; l3 = lc[tid + 3 * kTileNodes]; }
+        double xown = 0.0, bi = 0.0, di = 0.0, dprev = 0.0;
+        if (tid < nrows) {
+          const int row = n0 + tid;
+          xown = __ldcg(xin + row);
+          xs[tid] = xown;
+          bi = a.b[row];
+          di = a.dinv[row];
+          if (!first) dprev = a.d[row];
+        }
+        for (int e = tid; e < ne; e += kTileNodes) {
+          const int cc = a.tile_ext[e0 + e];
+          xs[kTileNodes + e] = (GHOST && cc >= no) ? ll_load(ll + 2 * (size_t)(cc - no), tag, a.error) : __ldcg(xin + cc);
+        }
+        __syncthreads();
+        if (tid < cnt) prod[tid] = v0 * xs[l0];
+        if (tid + kTileNodes < cnt) prod[tid + kTileNodes] = v1 * xs[l1];
+        if (tid + 2 * kTileNodes < cnt) prod[tid + 2 * kTileNodes] = v2 * xs[l2];
+        if (tid + 3 * kTileNodes < cnt) prod[tid + 3 * kTileNodes] = v3 * xs[l3];
+        for (int p = tid + 4 * kTileNodes; p < cnt; p += kTileNodes) prod[p] = v[p] * xs[lc[p]];
+        __syncthreads();
+        if (tid < nrows) {
+          const int row = n0 + tid;
+          double s = 0.0;
+          for (int k = rp[tid]; k < rp[tid + 1]; ++k) s += prod[k];
+          const double r = bi - s, z = di * r;
+          const double dk = first ? c2 * z : c1 * dprev + c2 * z;
+          a.d[row] = dk;
+          xout[row] = xown + dk;
+          if (last) zz += z * z;
+          if (first) bb += (di * bi) * (di * bi);
+        }
+        __syncthreads();
+      }
+    }
+    if (!last) grid_sync(a.bar, a.status, a.error, nblk, gen);
+  }
+  // ---- the norms: ||D^-1 (b - M x_{last input})||^2 and, when this launch started the solve, ||D^-1 b||^2
+  if (!comm_cta) {
+    zz = block_sum(zz, red);
+    bb = block_sum(bb, red);
+    if (tid == 0) {
+      a.part[(size_t)PP_RR * kMaxPartials + wid] = zz;
+      a.part[(size_t)PP_BB * kMaxPartials + wid] = bb;
+    }
+  }
+  BicgArgs ba{};   // grid_reduce reads only these fields
+  ba.bar = a.bar; ba.status = a.status; ba.error = a.error; ba.dev = a.dev; ba.tim = a.tim;
+  Slots<2> sl;
+  sl.p[0] = a.part + (size_t)PP_RR * kMaxPartials;
+  sl.p[1] = a.part + (size_t)PP_BB * kMaxPartials;
+  grid_reduce<2>(ba, nblk, nwork, sl, a.red_seq0 + 1, a.scalars + PS_D0, sums, gen);
+  if (blockIdx.x == 0 && tid == 0) {
+    const double gbb = a.first ? sums[1] : a.scalars[PS_BB];
+    if (a.first) a.scalars[PS_BB] = gbb;
+    a.scalars[PS_RR] = sums[0];
+    a.scalars[PS_RELRES] = gbb > 0.0 ? sqrt(sums[0] / gbb) : sqrt(sums[0]);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct PersistPlan { int grid = 0, grid_cheb = 0; size_t smem = 0; bool ok = false, tried = false, ghost = false; };
+
+template <class K>
+static int plan_kernel(cfem_ctx* c, K kern, size_t smem, bool ghost) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTileNodes, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return 0; }
+  int64_t grid = (int64_t)occ * c->sm_count;
+  const int64_t want = c->dm.ntiles + (ghost ? 1 : 0);
+  if (grid > want) grid = want;
+  if (grid > kMaxPartials) grid = kMaxPartials;
+  if (grid < (ghost ? 2 : 1)) return 0;
+  return (int)grid;
+}
+
+static bool persist_plan(cfem_ctx* c) {
   PersistPlan* pl = (PersistPlan*)c->persist_plan;
   if (!pl) { pl = new PersistPlan(); c->persist_plan = pl; }
   if (!pl->tried) {
     pl->tried = true;
-    pl->ok = c->world > 1 ? plan_one<true>(c, *pl) : plan_one<false>(c, *pl);
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+    // CFEM_FORCE_GHOST=1 runs the distributed kernel variants on one GPU (no peers): isolates their own cost
+    pl->ghost = c->world > 1 || getenv("CFEM_FORCE_GHOST") != nullptr;
+    pl->smem = sizeof(double) * ((size_t)kTileNnzCap + kTileNodes + c->dm.ext_cap);
+    if (coop) {
+      pl->grid = pl->ghost ? plan_kernel(c, k_bicg_persist<true>, pl->smem, true) : plan_kernel(c, k_bicg_persist<false>, pl->smem, false);
+      pl->grid_cheb = pl->ghost ? plan_kernel(c, k_cheb_persist<true>, pl->smem, true) : plan_kernel(c, k_cheb_persist<false>, pl->smem, false);
+    }
+    pl->ok = pl->grid > 0 && pl->grid_cheb > 0 && (c->world == 1 || c->p2p != nullptr);
   }
   return pl->ok;
+}
+
+bool bicgstab_persist_available(cfem_ctx* c) {
+  static const bool off = getenv("CFEM_BICGSTAB") && std::string(getenv("CFEM_BICGSTAB")) != "persist";
+  return !off && persist_plan(c);
+}
+
+// opt-in (CFEM_CHEB=persist): measured SLOWER than the chain of T16 launches (33 vs 26 us per iteration at 1 M rows on
+// one GPU, 0.97 vs 0.79 ms per step on two) -- the iteration has no reduction to fold into the barrier, the chain
+// already overlaps its launches programmatically, and the cooperative kernel runs at 4 instead of 6 CTAs per SM
+bool cheb_persist_available(cfem_ctx* c) {
+  static const bool on = getenv("CFEM_CHEB") && std::string(getenv("CFEM_CHEB")) == "persist";
+  return on && persist_plan(c);
 }
 
 void persist_plan_free(cfem_ctx* c) {
@@ -388,12 +579,40 @@ void launch_bicg_persist(cfem_ctx* c, const Matrix& A, const double* rhat, doubl
   a.bar = (unsigned int*)(c->status + 5);
   a.rtol2 = rtol2; a.atol2 = atol2; a.max_it = max_it;
   CUDA_OK(cudaMemsetAsync(c->status + 3, 0, 4 * sizeof(int32_t), c->stream));   // time-out flag, fin ticket, barrier words
-  persist_comm_args(c, &a.dev, &a.mailbox, &a.halo_off, &a.halo_stride, &a.peer_rank, &a.npeer, &a.error, &a.halo_seq0, &a.red_seq0);
+  persist_comm_args(c, &a.dev, &a.mailbox, &a.halo_off, &a.halo_stride, &a.peer_rank, &a.npeer, &a.error, &a.halo_seq0, &a.red_seq0, &a.tim);
   void* args[] = {(void*)&a};
-  if (c->world > 1)
+  if (pl->ghost)
     CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_bicg_persist<true>, dim3(pl->grid), dim3(kTileNodes), args, pl->smem, c->stream));
   else
     CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_bicg_persist<false>, dim3(pl->grid), dim3(kTileNodes), args, pl->smem, c->stream));
+  c->launches.total++;
+  c->launches.spmv++;
+}
+
+// `iters` Chebyshev iterations starting from x_in (result in x_in when iters is even, else in x_other); the
+// row-equilibrated relative residual of the LAST iteration's input lands in scalars[S_RELRES].
+void launch_cheb_persist(cfem_ctx* c, const Matrix& A, const double* b, double* x_in, double* x_other, double* d,
+                         bool first, int iters, double rho0, double sigma1, double theta, double delta) {
+  PersistPlan* pl = (PersistPlan*)c->persist_plan;
+  ChebArgs a{};
+  const DevMesh& m = c->dm;
+  a.no = m.no; a.ntiles = m.ntiles; a.n_interior = m.n_interior; a.ext_cap = m.ext_cap;
+  a.tile_order = m.tile_order; a.tile_node = m.tile_node; a.rowptr = m.rowptr; a.tile_extptr = m.tile_extptr;
+  a.tile_ext = m.tile_ext; a.lc16 = m.lc16;
+  a.vals = A.vals; a.dinv = A.dinv; a.b = b;
+  a.x0 = x_in; a.x1 = x_other; a.d = d;
+  a.part = c->partials; a.scalars = c->scalars; a.status = c->status;
+  a.bar = (unsigned int*)(c->status + 5);
+  a.first = first ? 1 : 0; a.iters = iters;
+  a.rho0 = rho0; a.sigma1 = sigma1; a.theta = theta; a.delta = delta;
+  CUDA_OK(cudaMemsetAsync(c->status + 3, 0, 4 * sizeof(int32_t), c->stream));
+  persist_comm_args(c, &a.dev, &a.mailbox, &a.halo_off, &a.halo_stride, &a.peer_rank, &a.npeer, &a.error, &a.halo_seq0, &a.red_seq0, &a.tim);
+  void* args[] = {(void*)&a};
+  if (pl->ghost)
+    CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_cheb_persist<true>, dim3(pl->grid_cheb), dim3(kTileNodes), args, pl->smem, c->stream));
+  else
+    CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_cheb_persist<false>, dim3(pl->grid_cheb), dim3(kTileNodes), args, pl->smem, c->stream));
+  persist_comm_advance(c, iters, 1);
   c->launches.total++;
   c->launches.spmv++;
 }

@@ -40,34 +40,54 @@ static void sort_pairs(It b, It e) {
 #endif
 }
 
-// Whole-mesh relations in global internal numbering.
-struct GlobalMesh {
+// ---- stage A: what every rank computes for the WHOLE mesh (light: a few passes and one sort) ------------------
+struct GlobalOrder {
   int64_t nn = 0, nc = 0;
-  std::vector<int32_t> n2u, u2n;
-  std::vector<double> xy;
-  std::vector<int32_t> cells;    // 3*nc, sorted by smallest vertex
-  std::vector<int32_t> cell_user;  // nc, the caller's index of each sorted cell
-  std::vector<int32_t> v2c_ptr;  // nn+1
-  std::vector<int32_t> v2c;      // 3*nc  cell of each (vertex, incident cell) pair, ascending
-  std::vector<uint8_t> v2k;      // 3*nc  local vertex number in that cell
-  std::vector<int32_t> rowptr, colidx;
-  std::vector<uint8_t> is_bnd;
-  int max_row = 0;
+  std::vector<int32_t> n2u, u2n;       // global internal <-> caller numbering
+  std::vector<int64_t> part_off;       // world+1 offsets into the internal order
+  std::vector<uint8_t> is_bnd_user;    // boundary flag per caller node
 };
 
-static void global_analysis(GlobalMesh& g, int64_t nn, int64_t nc, const double* x, int xdim,
-                            const void* cells_in, int idx_bytes, int order) {
+static inline uint64_t mix64(uint64_t z) {  // splitmix64 finaliser: a bijection, so distinct nodes get distinct keys
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+template <class I>
+static inline int64_t cell_vertex(const void* cells, int64_t c, int k) { return (int64_t)((const I*)cells)[3 * c + k]; }
+
+// Node ordering (Hilbert curve, or caller order), the partition of that order into one contiguous range per rank
+// (equal ranges, or -- node_part given -- the caller's parts, e.g. from METIS, each kept in Hilbert order), and the
+// boundary nodes of the mesh.
+static void global_order(GlobalOrder& g, int64_t nn, int64_t nc, const double* x, int xdim, const void* cells_in,
+                         int idx_bytes, int order, int world, const int32_t* node_part) {
   if (nn <= 0 || nc <= 0) CFEM_THROW(-1, "empty mesh");
   if (nn >= (int64_t)1 << 31 || 3 * nc >= (int64_t)1 << 31) CFEM_THROW(-1, "mesh too large for int32 indices");
   if (xdim != 2 && xdim != 3) CFEM_THROW(-1, "xdim must be 2 or 3");
   if (idx_bytes != 4 && idx_bytes != 8) CFEM_THROW(-1, "cell_index_bytes must be 4 or 8");
   g.nn = nn;
   g.nc = nc;
-
   // ---- 1. node ordering ----------------------------------------------------
   g.n2u.resize(nn);
   g.u2n.resize(nn);
-  if (order == CFEM_ORDER_NATURAL) {
+  g.part_off.assign(world + 1, 0);
+  if (node_part) {
+    for (int64_t i = 0; i < nn; ++i) {
+      if (node_part[i] < 0 || node_part[i] >= world) CFEM_THROW(-1, "node_part entry out of range");
+      g.part_off[node_part[i] + 1]++;
+    }
+    for (int r = 0; r < world; ++r) {
+      if (g.part_off[r + 1] == 0) CFEM_THROW(-1, "a rank owns no node: empty part in node_part");
+      g.part_off[r + 1] += g.part_off[r];
+    }
+  } else {
+    for (int r = 0; r <= world; ++r) g.part_off[r] = (int64_t)((__int128)nn * r / world);
+    for (int r = 0; r < world; ++r)
+      if (g.part_off[r + 1] <= g.part_off[r]) CFEM_THROW(-1, "a rank owns no node: mesh too small for this many ranks");
+  }
+  if (order == CFEM_ORDER_NATURAL && !node_part) {
     std::iota(g.n2u.begin(), g.n2u.end(), 0);
   } else {
     double xmin = x[0], xmax = x[0], ymin = x[1], ymax = x[1];
@@ -80,12 +100,20 @@ static void global_analysis(GlobalMesh& g, int64_t nn, int64_t nc, const double*
     const int bits = 24;
     const double span = std::max(std::max(xmax - xmin, ymax - ymin), 1e-300);
     const double scale = (double)((1u << bits) - 1) / span;
+    const bool hilbert = order != CFEM_ORDER_NATURAL;
     std::vector<std::pair<uint64_t, int32_t>> keys(nn);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < nn; ++i) {
-      const uint32_t qx = (uint32_t)((x[i * xdim] - xmin) * scale);
-      const uint32_t qy = (uint32_t)((x[i * xdim + 1] - ymin) * scale);
-      keys[i] = {hilbert_key(qx, qy, bits), (int32_t)i};
+      uint64_t k;
+      if (hilbert) {
+        const uint32_t qx = (uint32_t)((x[i * xdim] - xmin) * scale);
+        const uint32_t qy = (uint32_t)((x[i * xdim + 1] - ymin) * scale);
+        k = hilbert_key(qx, qy, bits);   // < 2^48
+      } else {
+        k = (uint64_t)i;
+      }
+      if (node_part) k |= (uint64_t)node_part[i] << 48;   // parts first, each in curve order
+      keys[i] = {k, (int32_t)i};
     }
     sort_pairs(keys.begin(), keys.end());
 #pragma omp parallel for schedule(static)
@@ -93,159 +121,111 @@ static void global_analysis(GlobalMesh& g, int64_t nn, int64_t nc, const double*
   }
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < nn; ++i) g.u2n[g.n2u[i]] = (int32_t)i;
-  g.xy.resize(2 * nn);
-#pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < nn; ++i) {
-    const int64_t u = g.n2u[i];
-    g.xy[2 * i] = x[u * xdim];
-    g.xy[2 * i + 1] = x[u * xdim + 1];
-  }
 
-  // ---- 2. cells -> internal ids, ordered by their smallest vertex -----------
-  std::vector<int32_t> ctmp(3 * nc);
-  {
-    bool range_bad = false, rep_bad = false;
+  // ---- 2. connectivity checks + boundary nodes, one pass over the cells, no relation built ------------------
+  // Around a node every neighbour appears once per cell that contains the edge to it: twice for an interior edge,
+  // once for a boundary edge.  XOR-ing a bijective 64-bit key of the two other vertices of each incident cell
+  // therefore leaves 0 exactly for nodes without a boundary edge.
+  std::vector<uint64_t> acc(nn, 0);
+  std::vector<uint8_t> touched(nn, 0);
+  bool range_bad = false, rep_bad = false;
 #pragma omp parallel for schedule(static) reduction(|| : range_bad) reduction(|| : rep_bad)
-    for (int64_t c = 0; c < nc; ++c) {
-      for (int k = 0; k < 3; ++k) {
-        int64_t v = idx_bytes == 4 ? (int64_t)((const int32_t*)cells_in)[3 * c + k]
-                                   : (int64_t)((const int64_t*)cells_in)[3 * c + k];
-        if (v < 0 || v >= nn) { range_bad = true; v = 0; }
-        ctmp[3 * c + k] = g.u2n[v];
-      }
-      if (ctmp[3 * c] == ctmp[3 * c + 1] || ctmp[3 * c] == ctmp[3 * c + 2] || ctmp[3 * c + 1] == ctmp[3 * c + 2])
-        rep_bad = true;
+  for (int64_t c = 0; c < nc; ++c) {
+    int64_t v[3];
+    for (int k = 0; k < 3; ++k) {
+      v[k] = idx_bytes == 4 ? cell_vertex<int32_t>(cells_in, c, k) : cell_vertex<int64_t>(cells_in, c, k);
+      if (v[k] < 0 || v[k] >= nn) { range_bad = true; v[k] = 0; }
     }
-    if (range_bad) CFEM_THROW(-1, "cell connectivity has an out-of-range vertex");
-    if (rep_bad) CFEM_THROW(-1, "cell connectivity has a repeated vertex");
+    if (v[0] == v[1] || v[0] == v[2] || v[1] == v[2]) rep_bad = true;
+    const uint64_t h0 = mix64((uint64_t)v[0]), h1 = mix64((uint64_t)v[1]), h2 = mix64((uint64_t)v[2]);
+    const uint64_t a0 = h1 ^ h2, a1 = h0 ^ h2, a2 = h0 ^ h1;
+    // XOR commutes: the result does not depend on the order in which the threads get here
+#pragma omp atomic
+    acc[v[0]] ^= a0;
+#pragma omp atomic
+    acc[v[1]] ^= a1;
+#pragma omp atomic
+    acc[v[2]] ^= a2;
+    touched[v[0]] = touched[v[1]] = touched[v[2]] = 1;   // benign same-value races
   }
-  g.cells.resize(3 * nc);
-  g.cell_user.resize(nc);
-  {
-    std::vector<int32_t> cnt(nn + 1, 0);  // counting sort by min vertex (stable -> deterministic)
-    for (int64_t c = 0; c < nc; ++c)
-      cnt[std::min(ctmp[3 * c], std::min(ctmp[3 * c + 1], ctmp[3 * c + 2])) + 1]++;
-    for (int64_t i = 0; i < nn; ++i) cnt[i + 1] += cnt[i];
-    for (int64_t c = 0; c < nc; ++c) {
-      const int32_t m = std::min(ctmp[3 * c], std::min(ctmp[3 * c + 1], ctmp[3 * c + 2]));
-      const int64_t p = cnt[m]++;
-      g.cells[3 * p] = ctmp[3 * c];
-      g.cells[3 * p + 1] = ctmp[3 * c + 1];
-      g.cells[3 * p + 2] = ctmp[3 * c + 2];
-      g.cell_user[p] = (int32_t)c;
-    }
-  }
-  std::vector<int32_t>().swap(ctmp);
-
-  // ---- 3. vertex -> (cell, k), cells ascending ------------------------------
-  g.v2c_ptr.assign(nn + 1, 0);
-  for (int64_t e = 0; e < 3 * nc; ++e) g.v2c_ptr[g.cells[e] + 1]++;
+  if (range_bad) CFEM_THROW(-1, "cell connectivity has an out-of-range vertex");
+  if (rep_bad) CFEM_THROW(-1, "cell connectivity has a repeated vertex");
+  g.is_bnd_user.resize(nn);
   for (int64_t i = 0; i < nn; ++i) {
-    if (g.v2c_ptr[i + 1] == 0)
-      CFEM_THROW(-1, "mesh has a node that belongs to no cell (node " + std::to_string(g.n2u[i]) + ")");
-    g.v2c_ptr[i + 1] += g.v2c_ptr[i];
+    if (!touched[i]) CFEM_THROW(-1, "mesh has a node that belongs to no cell (node " + std::to_string(i) + ")");
+    g.is_bnd_user[i] = acc[i] != 0;
   }
-  g.v2c.resize(3 * nc);
-  g.v2k.resize(3 * nc);
-  {
-    std::vector<int32_t> fill(g.v2c_ptr.begin(), g.v2c_ptr.end() - 1);
-    for (int64_t c = 0; c < nc; ++c)
-      for (int k = 0; k < 3; ++k) {
-        const int64_t p = fill[g.cells[3 * c + k]]++;
-        g.v2c[p] = (int32_t)c;
-        g.v2k[p] = (uint8_t)k;
-      }
-  }
-
-  // ---- 4. CSR pattern (sorted rows) + boundary flags ------------------------
-  g.rowptr.assign(nn + 1, 0);
-  int max_row = 0;
-  bool row_overflow = false;
-#pragma omp parallel for schedule(static) reduction(max : max_row) reduction(|| : row_overflow)
-  for (int64_t i = 0; i < nn; ++i) {
-    int32_t buf[3 * 64];
-    const int deg = g.v2c_ptr[i + 1] - g.v2c_ptr[i];
-    if (deg > 64) { row_overflow = true; continue; }
-    int m = 0;
-    for (int e = g.v2c_ptr[i]; e < g.v2c_ptr[i + 1]; ++e)
-      for (int k = 0; k < 3; ++k) buf[m++] = g.cells[3 * (int64_t)g.v2c[e] + k];
-    std::sort(buf, buf + m);
-    const int len = (int)(std::unique(buf, buf + m) - buf);
-    g.rowptr[i + 1] = len;
-    max_row = std::max(max_row, len);
-  }
-  if (row_overflow || max_row > kMaxRow)
-    CFEM_THROW(-1, "a node has more than " + std::to_string(kMaxRow - 1) + " neighbours; unsupported mesh");
-  for (int64_t i = 0; i < nn; ++i) g.rowptr[i + 1] += g.rowptr[i];
-  g.max_row = max_row;
-  g.colidx.resize(g.rowptr[nn]);
-  g.is_bnd.assign(nn, 0);
-  std::vector<uint8_t> bnd_edge_flag(g.rowptr[nn], 0);
-#pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < nn; ++i) {
-    int32_t buf[3 * 64];
-    int m = 0;
-    for (int e = g.v2c_ptr[i]; e < g.v2c_ptr[i + 1]; ++e)
-      for (int k = 0; k < 3; ++k) buf[m++] = g.cells[3 * (int64_t)g.v2c[e] + k];
-    std::sort(buf, buf + m);
-    // run lengths: neighbour j shares (count) cells with i; exactly 1 => boundary edge
-    int32_t* row = &g.colidx[g.rowptr[i]];
-    int len = 0;
-    for (int a = 0; a < m;) {
-      int b = a;
-      while (b < m && buf[b] == buf[a]) ++b;
-      row[len] = buf[a];
-      if (buf[a] != (int32_t)i && (b - a) == 1) bnd_edge_flag[g.rowptr[i] + len] = 1;
-      ++len;
-      a = b;
-    }
-  }
-  for (int64_t i = 0; i < nn; ++i)
-    for (int p = g.rowptr[i]; p < g.rowptr[i + 1]; ++p)
-      if (bnd_edge_flag[p]) { g.is_bnd[i] = 1; g.is_bnd[g.colidx[p]] = 1; }
 }
 
-// Restrict the global relations to rank's contiguous range of the curve plus one ghost layer.
-static void build_local(const GlobalMesh& g, int rank, int world, HostMesh& hm, std::vector<int32_t>& lv2c,
-                        std::vector<uint8_t>& lv2k) {
-  const int64_t nn = g.nn;
+// ---- stage B: rank's part (contiguous range [lo, hi) of the internal order) plus one ghost layer -----------
+// Everything heavy (cell list, adjacency, CSR pattern) is built for the part only: O(N / world) memory and time on top
+// of the light global stage.
+static void build_part(const GlobalOrder& g, const double* x, int xdim, const void* cells_in, int idx_bytes, int rank,
+                       int world, HostMesh& hm, std::vector<int32_t>& lv2c, std::vector<uint8_t>& lv2k) {
+  const int64_t nn = g.nn, ncg = g.nc;
   hm.rank = rank;
   hm.world = world;
   hm.nn_global = nn;
-  hm.part_off.resize(world + 1);
-  for (int r = 0; r <= world; ++r) hm.part_off[r] = (int64_t)((__int128)nn * r / world);
+  hm.part_off = g.part_off;
   const int64_t lo = hm.part_off[rank], hi = hm.part_off[rank + 1];
   const int64_t no = hi - lo;
-  if (no <= 0) CFEM_THROW(-1, "a rank owns no node: mesh too small for this many ranks");
   hm.n_owned = no;
-  hm.max_row = g.max_row;
   auto owner_of = [&](int32_t node) {
     return (int)(std::upper_bound(hm.part_off.begin(), hm.part_off.end(), (int64_t)node) - hm.part_off.begin()) - 1;
   };
 
-  // local cells: every cell touching an owned node, ascending global order
-  std::vector<int32_t> lcells;
-  if (world == 1) {
-    lcells.resize(g.nc);
-    std::iota(lcells.begin(), lcells.end(), 0);
-  } else {
-    std::vector<uint8_t> mark(g.nc, 0);
-    for (int64_t e = g.v2c_ptr[lo]; e < g.v2c_ptr[hi]; ++e) mark[g.v2c[e]] = 1;
-    for (int64_t c = 0; c < g.nc; ++c)
-      if (mark[c]) lcells.push_back((int32_t)c);
+  // local cells: every cell touching an owned node, ordered by (smallest internal vertex, caller index)
+  struct LCell { int32_t vmin, user, v[3]; };
+  std::vector<LCell> lc;
+  {
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    std::vector<std::vector<LCell>> found(nthreads);   // per thread; the sort below fixes the order
+#pragma omp parallel
+    {
+      int tid = 0;
+#ifdef _OPENMP
+      tid = omp_get_thread_num();
+#endif
+      std::vector<LCell>& mine_cells = found[tid];
+#pragma omp for schedule(static)
+      for (int64_t c = 0; c < ncg; ++c) {
+        LCell e;
+        bool mine = false;
+        for (int k = 0; k < 3; ++k) {
+          const int64_t u = idx_bytes == 4 ? cell_vertex<int32_t>(cells_in, c, k) : cell_vertex<int64_t>(cells_in, c, k);
+          e.v[k] = g.u2n[u];
+          mine = mine || (e.v[k] >= lo && e.v[k] < hi);
+        }
+        if (!mine) continue;
+        e.vmin = std::min(e.v[0], std::min(e.v[1], e.v[2]));
+        e.user = (int32_t)c;
+        mine_cells.push_back(e);
+      }
+    }
+    size_t total = 0;
+    for (auto& f : found) total += f.size();
+    lc.reserve(total);
+    for (auto& f : found) { lc.insert(lc.end(), f.begin(), f.end()); std::vector<LCell>().swap(f); }
   }
-  const int64_t nc = (int64_t)lcells.size();
+  auto cell_less = [](const LCell& a, const LCell& b) { return a.vmin != b.vmin ? a.vmin < b.vmin : a.user < b.user; };
+#ifdef _OPENMP
+  __gnu_parallel::sort(lc.begin(), lc.end(), cell_less);
+#else
+  std::sort(lc.begin(), lc.end(), cell_less);
+#endif
+  const int64_t nc = (int64_t)lc.size();
   hm.nc = nc;
 
-  // ghosts: vertices of local cells outside [lo, hi), ascending global id (=> grouped by owner)
+  // ghosts: vertices of local cells outside [lo, hi), ascending internal id (=> grouped by owner)
   std::vector<int32_t> ghosts;
   if (world > 1) {
     for (int64_t c = 0; c < nc; ++c)
-      for (int k = 0; k < 3; ++k) {
-        const int32_t v = g.cells[3 * (int64_t)lcells[c] + k];
-        if (v < lo || v >= hi) ghosts.push_back(v);
-      }
-    std::sort(ghosts.begin(), ghosts.end());
+      for (int k = 0; k < 3; ++k)
+        if (lc[c].v[k] < lo || lc[c].v[k] >= hi) ghosts.push_back(lc[c].v[k]);
+    sort_pairs(ghosts.begin(), ghosts.end());
     ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
   }
   const int64_t ng = (int64_t)ghosts.size();
@@ -263,43 +243,74 @@ static void build_local(const GlobalMesh& g, int rank, int world, HostMesh& hm, 
   hm.is_bnd.resize(nl);
 #pragma omp parallel for schedule(static)
   for (int64_t l = 0; l < nl; ++l) {
-    const int32_t v = to_global(l);
-    hm.n2u[l] = g.n2u[v];
-    hm.xy[2 * l] = g.xy[2 * (int64_t)v];
-    hm.xy[2 * l + 1] = g.xy[2 * (int64_t)v + 1];
-    hm.is_bnd[l] = g.is_bnd[v];
+    const int64_t u = g.n2u[to_global(l)];
+    hm.n2u[l] = (int32_t)u;
+    hm.xy[2 * l] = x[u * xdim];
+    hm.xy[2 * l + 1] = x[u * xdim + 1];
+    hm.is_bnd[l] = g.is_bnd_user[u];
   }
   hm.u2n = g.u2n;  // user -> GLOBAL internal id (only meaningful together with part_off)
   hm.cells.resize(3 * nc);
 #pragma omp parallel for schedule(static)
   for (int64_t c = 0; c < nc; ++c)
-    for (int k = 0; k < 3; ++k) hm.cells[3 * c + k] = to_local(g.cells[3 * (int64_t)lcells[c] + k]);
+    for (int k = 0; k < 3; ++k) hm.cells[3 * c + k] = to_local(lc[c].v[k]);
 
-  // owned rows, columns kept in ascending GLOBAL order (so every rank count sums a row in the same order)
-  hm.rowptr.resize(no + 1);
-  for (int64_t i = 0; i <= no; ++i) hm.rowptr[i] = g.rowptr[lo + i] - g.rowptr[lo];
-  hm.nnz = hm.rowptr[no];
-  hm.colidx.resize(hm.nnz);
-#pragma omp parallel for schedule(static)
-  for (int64_t p = 0; p < hm.nnz; ++p) hm.colidx[p] = to_local(g.colidx[g.rowptr[lo] + p]);
-
-  // vertex -> cell adjacency of owned nodes, local cell ids
-  hm.v2c_ptr.resize(no + 1);
-  for (int64_t i = 0; i <= no; ++i) hm.v2c_ptr[i] = g.v2c_ptr[lo + i] - g.v2c_ptr[lo];
+  // vertex -> (cell, k) of the owned nodes, cells ascending
+  hm.v2c_ptr.assign(no + 1, 0);
+  for (int64_t e = 0; e < 3 * nc; ++e)
+    if (hm.cells[e] < no) hm.v2c_ptr[hm.cells[e] + 1]++;
+  for (int64_t i = 0; i < no; ++i) hm.v2c_ptr[i + 1] += hm.v2c_ptr[i];
   const int64_t ne = hm.v2c_ptr[no];
   lv2c.resize(ne);
   lv2k.resize(ne);
-  if (world == 1) {
-    lv2c = g.v2c;
-    lv2k = g.v2k;
-  } else {
-#pragma omp parallel for schedule(static)
-    for (int64_t e = 0; e < ne; ++e) {
-      const int32_t gc = g.v2c[g.v2c_ptr[lo] + e];
-      lv2c[e] = (int32_t)(std::lower_bound(lcells.begin(), lcells.end(), gc) - lcells.begin());
-      lv2k[e] = g.v2k[g.v2c_ptr[lo] + e];
-    }
+  {
+    std::vector<int32_t> fill(hm.v2c_ptr.begin(), hm.v2c_ptr.end() - 1);
+    for (int64_t c = 0; c < nc; ++c)
+      for (int k = 0; k < 3; ++k) {
+        const int32_t v = hm.cells[3 * c + k];
+        if (v >= no) continue;
+        const int64_t p = fill[v]++;
+        lv2c[p] = (int32_t)c;
+        lv2k[p] = (uint8_t)k;
+      }
   }
+
+  // owned rows of the P1 pattern (== node patches), columns in ascending GLOBAL order so that every rank count
+  // sums a row in the same order
+  hm.rowptr.assign(no + 1, 0);
+  int max_row = 0;
+  bool row_overflow = false;
+#pragma omp parallel for schedule(static) reduction(max : max_row) reduction(|| : row_overflow)
+  for (int64_t i = 0; i < no; ++i) {
+    int32_t buf[3 * 64];
+    const int deg = hm.v2c_ptr[i + 1] - hm.v2c_ptr[i];
+    if (deg > 64) { row_overflow = true; continue; }
+    int m = 0;
+    for (int e = hm.v2c_ptr[i]; e < hm.v2c_ptr[i + 1]; ++e)
+      for (int k = 0; k < 3; ++k) buf[m++] = lc[lv2c[e]].v[k];
+    std::sort(buf, buf + m);
+    const int len = (int)(std::unique(buf, buf + m) - buf);
+    hm.rowptr[i + 1] = len;
+    max_row = std::max(max_row, len);
+  }
+  if (row_overflow || max_row > kMaxRow)
+    CFEM_THROW(-1, "a node has more than " + std::to_string(kMaxRow - 1) + " neighbours; unsupported mesh");
+  for (int64_t i = 0; i < no; ++i) hm.rowptr[i + 1] += hm.rowptr[i];
+  hm.max_row = max_row;
+  hm.nnz = hm.rowptr[no];
+  hm.colidx.resize(hm.nnz);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < no; ++i) {
+    int32_t buf[3 * 64];
+    int m = 0;
+    for (int e = hm.v2c_ptr[i]; e < hm.v2c_ptr[i + 1]; ++e)
+      for (int k = 0; k < 3; ++k) buf[m++] = lc[lv2c[e]].v[k];
+    std::sort(buf, buf + m);
+    const int len = (int)(std::unique(buf, buf + m) - buf);
+    int32_t* row = &hm.colidx[hm.rowptr[i]];
+    for (int a = 0; a < len; ++a) row[a] = to_local(buf[a]);
+  }
+
   // per owned node the incident cell with the highest caller index: a per-cell loop that writes a cell
   // value to its three dofs (Code/Linear_advection/RV_cell.py:190-192) leaves exactly that cell's value
   hm.last_cell.resize(no);
@@ -307,7 +318,7 @@ static void build_local(const GlobalMesh& g, int rank, int world, HostMesh& hm, 
   for (int64_t i = 0; i < no; ++i) {
     int32_t best = -1, best_user = -1;
     for (int e = hm.v2c_ptr[i]; e < hm.v2c_ptr[i + 1]; ++e) {
-      const int32_t cu = g.cell_user[g.v2c[g.v2c_ptr[lo] + e]];
+      const int32_t cu = lc[lv2c[e]].user;
       if (cu > best_user) { best_user = cu; best = lv2c[e]; }
     }
     hm.last_cell[i] = best;
@@ -315,9 +326,8 @@ static void build_local(const GlobalMesh& g, int rank, int world, HostMesh& hm, 
 
   // boundary dofs in caller numbering: global list (every rank reports the same set)
   hm.bnd_user_sorted.clear();
-  for (int64_t i = 0; i < nn; ++i)
-    if (g.is_bnd[i]) hm.bnd_user_sorted.push_back(g.n2u[i]);
-  std::sort(hm.bnd_user_sorted.begin(), hm.bnd_user_sorted.end());
+  for (int64_t u = 0; u < nn; ++u)
+    if (g.is_bnd_user[u]) hm.bnd_user_sorted.push_back((int32_t)u);
 
   // halo exchange lists
   hm.peer_rank.clear();
@@ -329,24 +339,23 @@ static void build_local(const GlobalMesh& g, int rank, int world, HostMesh& hm, 
     std::vector<std::vector<int32_t>> send(world);
     for (int64_t c = 0; c < nc; ++c) {
       int own[3];
-      int32_t v[3];
-      for (int k = 0; k < 3; ++k) { v[k] = g.cells[3 * (int64_t)lcells[c] + k]; own[k] = owner_of(v[k]); }
+      for (int k = 0; k < 3; ++k) own[k] = owner_of(lc[c].v[k]);
       for (int a = 0; a < 3; ++a)
         if (own[a] == rank)
           for (int b = 0; b < 3; ++b)
-            if (own[b] != rank) send[own[b]].push_back(v[a]);
+            if (own[b] != rank) send[own[b]].push_back(lc[c].v[a]);
     }
     std::vector<int64_t> rcnt(world, 0), roff(world, 0);
     for (int64_t k = 0; k < ng; ++k) rcnt[owner_of(ghosts[k])]++;
-    int64_t acc = 0;
-    for (int r = 0; r < world; ++r) { roff[r] = acc; acc += rcnt[r]; }
+    int64_t accum = 0;
+    for (int r = 0; r < world; ++r) { roff[r] = accum; accum += rcnt[r]; }
     for (int r = 0; r < world; ++r) {
-      auto& s = send[r];
-      std::sort(s.begin(), s.end());
-      s.erase(std::unique(s.begin(), s.end()), s.end());
-      if (s.empty() && rcnt[r] == 0) continue;
+      auto& sl = send[r];
+      std::sort(sl.begin(), sl.end());
+      sl.erase(std::unique(sl.begin(), sl.end()), sl.end());
+      if (sl.empty() && rcnt[r] == 0) continue;
       hm.peer_rank.push_back(r);
-      for (int32_t v : s) hm.send_idx.push_back((int32_t)(v - lo));
+      for (int32_t v : sl) hm.send_idx.push_back((int32_t)(v - lo));
       hm.send_ptr.push_back((int32_t)hm.send_idx.size());
       hm.recv_off.push_back((int32_t)(no + roff[r]));
       hm.recv_cnt.push_back((int32_t)rcnt[r]);
@@ -468,14 +477,15 @@ int32_t user_to_local(const HostMesh& hm, int64_t user_dof) {
 }
 
 void analyse_mesh(HostMesh& hm, int64_t nn, int64_t nc, const double* x, int xdim, const void* cells,
-                  int idx_bytes, int order, int rank, int world) {
+                  int idx_bytes, int order, int rank, int world, const int32_t* node_part) {
   if (world < 1 || rank < 0 || rank >= world) CFEM_THROW(-1, "bad rank / world size");
-  GlobalMesh g;
-  global_analysis(g, nn, nc, x, xdim, cells, idx_bytes, order);
   std::vector<int32_t> lv2c;
   std::vector<uint8_t> lv2k;
-  build_local(g, rank, world, hm, lv2c, lv2k);
-  g = GlobalMesh();  // release the global relations before tiling
+  {
+    GlobalOrder g;
+    global_order(g, nn, nc, x, xdim, cells, idx_bytes, order, world, node_part);
+    build_part(g, x, xdim, cells, idx_bytes, rank, world, hm, lv2c, lv2k);
+  }  // the global order is released before tiling (u2n lives on in hm)
   build_tiles(hm, lv2c, lv2k);
 }
 

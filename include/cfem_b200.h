@@ -84,9 +84,26 @@ int cfem_nccl_unique_id(void* out128);
 int cfem_create_distributed(cfem_ctx** out, int device, int rank, int world, const void* nccl_id128,
                             int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
                             const void* cells, int cell_index_bytes, int order);
+/* Same with the partition given by the caller: node_part[i] in [0, world) is the rank that owns caller node i
+ * (every rank passes the same array), e.g. from cfem_host_partition.  A part becomes a contiguous range of the
+ * internal order (nodes sorted by part, then along the Hilbert curve); node_part == NULL is cfem_create_distributed. */
+int cfem_create_partitioned(cfem_ctx** out, int device, int rank, int world, const void* nccl_unique_id_128,
+                            int64_t n_nodes, int64_t n_cells, const double* x, int xdim, const void* cells,
+                            int cell_index_bytes, int order, const int32_t* node_part);
+/* Graph partition of the mesh, host only: method CFEM_PART_METIS = METIS k-way on the nodal graph (the partitioner family
+ * dolfinx uses for the reference's MPI runs, Environment/fenicsx-env.yml:171,192); CFEM_PART_HILBERT = equal ranges
+ * of the Hilbert order (what node_part == NULL gives).  part_out: n_nodes entries, caller numbering. */
+enum { CFEM_PART_HILBERT = 0, CFEM_PART_METIS = 1 };
+int cfem_host_partition(int method, int world, int64_t n_nodes, int64_t n_cells, const double* x, int xdim,
+                        const void* cells, int cell_index_bytes, int32_t* part_out);
 int64_t cfem_num_owned(const cfem_ctx* ctx);
 int64_t cfem_num_ghosts(const cfem_ctx* ctx);
 int cfem_comm_stats(const cfem_ctx* ctx, int64_t* halo_exchanges, int64_t* allreduces, int64_t* halo_doubles_sent);
+/* Wait accounting of the peer-memory data plane since the last reset, measured on the device (no profiler):
+ * out[0..2] halo waits: total us over all waiting CTAs, number of waits, longest single wait (us);
+ * out[3..5] the cross-rank part of in-kernel all-reduces: total us, count, longest;
+ * out[6..7] time the first worker CTA of the persistent solver spent in grid barriers: total us, count. */
+int cfem_comm_timers(cfem_ctx* ctx, double out[8], int reset);
 void cfem_destroy(cfem_ctx* ctx);
 int cfem_synchronize(cfem_ctx* ctx);
 
@@ -306,6 +323,9 @@ int cfem_host_analyse(cfem_host_mesh** out, int64_t n_nodes, int64_t n_cells, co
 /* same, restricted to rank's part of a world-way partition (what cfem_create_distributed builds) */
 int cfem_host_analyse_part(cfem_host_mesh** out, int rank, int world, int64_t n_nodes, int64_t n_cells,
                            const double* x, int xdim, const void* cells, int cell_index_bytes, int order);
+int cfem_host_analyse_partitioned(cfem_host_mesh** out, int rank, int world, int64_t n_nodes, int64_t n_cells,
+                                  const double* x, int xdim, const void* cells, int cell_index_bytes, int order,
+                                  const int32_t* node_part);
 /* what: 0 owned nodes, 1 local nodes (owned + ghosts), 2 global nodes, 3 local cells, 4 nnz of owned rows */
 int64_t cfem_host_info(const cfem_host_mesh* hm, int what);
 /* number of elements of array `what` (4-byte elements except CFEM_HM_IS_BND: 1 byte, CFEM_HM_LC16: 2 bytes) */
