@@ -270,6 +270,11 @@ def main():
                     help="Krylov tolerance on the row-equilibrated residual; 1e-11 keeps the fields within 1e-10 of the "
                          "LU-based oracle with a decade to spare (tests/test_gpu_config_goldens.py runs the BASELINE configs at this setting)")
     ap.add_argument("--mass-rtol", type=float, default=1e-11, help="tolerance of the residual-projection (mass) solves")
+    ap.add_argument("--partition", default="hilbert", choices=["hilbert", "metis"],
+                    help="multi-GPU partition: equal ranges of the Hilbert order (default) or METIS k-way on the nodal graph")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the global mesh is n x n whatever the GPU count")
+    ap.add_argument("--sweep", action="store_true",
+                    help="scaling-sweep mode: device-resident timing only (no per-launch profile, end-to-end or CPU legs), one short JSON line")
     ap.add_argument("--no-parity", action="store_true", help="skip the small oracle-parity cases run before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solver", default="bicgstab", choices=["bicgstab", "gmres"],
@@ -304,6 +309,9 @@ def main():
     # weak scaling: every GPU keeps n x n cells; the global mesh is (a n) x (b n) cells on [0,a]x[0,b],
     # partitioned along the Hilbert curve (halo exchange + all-reduce over NCCL)
     a, b = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(world, (world, 1))
+    if args.strong:
+        a, b = 1, 1
+    t_setup = time.perf_counter()
     if args.workload == "burgers":
         x, c = meshes.rectangle(a * n, b * n, (0.0, 0.0), (float(a), float(b)))
     else:  # KPP on [-2,2]^2 scaled with the GPU grid, jittered + randomly renumbered (variant B)
@@ -311,9 +319,13 @@ def main():
     from cfem_b200 import distributed as D
 
     comm = D.make_comm(dist)
-    ctx = Context((x, c), device=local_rank, comm=comm)
+    t_mesh = time.perf_counter() - t_setup
+    part = D.make_partition(dist, x, c, "metis") if (world > 1 and args.partition == "metis") else None
+    t_ctx = time.perf_counter()
+    ctx = Context((x, c), device=local_rank, comm=comm, partition=part)
     nn = ctx.n   # global dofs
     ctx.nodal_h()   # h_CG stays resident in the context (with valid ghosts)
+    t_ctx = time.perf_counter() - t_ctx
     X3 = np.zeros((3, nn))
     X3[0], X3[1] = x[:, 0], x[:, 1]
     if args.workload == "burgers":
@@ -365,6 +377,25 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
     value = nn * K / (dev_ms * 1e-3)
+
+    if args.sweep:
+        if rank == 0:
+            print(json.dumps({
+                "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": dev_ms / K, "scaling": "strong" if args.strong else "weak",
+                "config": {"workload": wname, "dofs": nn, "cells": int(c.shape[0]), "dofs_per_gpu": nn // world,
+                           "partition": args.partition if world > 1 else None, "lin_rtol": args.lin_rtol,
+                           "mass_rtol": args.mass_rtol,
+                           "newton_its_per_step": st["newton_iterations"] / K,
+                           "krylov_its_per_step": st["krylov_iterations"] / K,
+                           "mass_its_per_step": st["mass_iterations"] / K,
+                           "comm": ctx.comm_stats() if world > 1 else None, "comm_wait": comm_wait,
+                           "n_ghosts_rank0": ctx.n_ghosts, "device_bytes_rank0": ctx.device_bytes,
+                           "mesh_generation_s": t_mesh, "context_setup_s_rank0": t_ctx},
+                "parity_rel_l2": parity, "gpu_launches": int(st["kernel_launches"]), "clocks": clk.summary()}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # ---- roofline leg: same K steps with every launch bracketed by CUDA events
     ctx.profile_begin(400000)
@@ -491,9 +522,9 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wname,
+        "config": {"workload": wname, "partition": args.partition if world > 1 else None,
                    "dofs": nn, "dofs_per_gpu": nn // world, "cells": int(c.shape[0]), "nnz": int(nnz), "dt": dt,
                    "Cvel": Cvel, "Crv": Crv, "residual_scheme": "bdf2", "newton_rtol": 1e-4,
                    "krylov": f"left-Jacobi {args.solver}, rtol {args.lin_rtol:g} on the row-equilibrated residual (stands in for LU); "

@@ -919,6 +919,7 @@ int cfem_step_advection(cfem_ctx* c, const cfem_step_params* p, int n_steps, int
     launch_adv_system(c, p->dt, c->w, gfem ? nullptr : c->eps, c->u_n, c->g, A, b);
     SolveResult rk = run_solver(c, p->solver, A, b, c->uh, p->lin_rtol, 0.0, p->lin_max_it, &c->krylov_predict);
     if (!rk.converged) CFEM_THROW(-3, "step_advection: Krylov solve did not converge");
+    halo_exchange(c, c->uh);   // the new solution feeds the next step's cell loops: ghosts needed
     st.krylov_iterations += rk.iters;
     if (gfem) {
       launch_copy(c, c->u_n, c->uh, nn);  // u_old keeps the initial condition (RV_node.py:157)

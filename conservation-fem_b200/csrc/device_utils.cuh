@@ -90,6 +90,53 @@ __device__ __forceinline__ double reduce_partials(const double* __restrict__ p, 
   return block_sum(s, sh);
 }
 
+// ---- per-CTA tile schedule of the SpMV-type kernels -------------------------------------------------------------
+// A CTA visits tiles  wid, wid + nwork, wid + 2 nwork, ... ("rounds") of tile_order.  What a tile needs before its first
+// data load -- tile id, row range, external-column range, CSR range -- is a chain of three dependent table loads;
+// fetched per tile it costs an L2 latency or two at every tile start (and one more in the distributed variants, which
+// go through tile_order).  fetch_tile_meta() resolves the chain for ALL rounds of the CTA at once (one thread per round)
+// into shared memory: one latency chain per launch -- or, in the persistent solvers, per solve.
+constexpr int kMetaRounds = 16;   // schedules longer than this fall back to per-tile fetches
+struct TileMeta { int t, n0, nrows, e0, ne, start, cnt; };
+
+// Order in which a CTA visits its rounds.  tile_order keeps the tiles with ghost columns at the end, i.e. in the last
+// round; the distributed variants visit that round in the MIDDLE, so the neighbours' halo values (pushed at the start
+// of the kernel / phase) have time to arrive and whatever wait remains is followed by more work of the same CTA.
+template <bool GHOST>
+__device__ __forceinline__ int round_of(const int kk, const int nrounds) {
+  if (!GHOST || nrounds < 3) return kk;
+  const int mid = nrounds / 2;
+  return kk == mid ? nrounds - 1 : (kk > mid ? kk - 1 : kk);
+}
+
+template <bool GHOST>
+__device__ __forceinline__ TileMeta tile_meta_of(const int kk, const int nrounds, const int wid, const int nwork,
+                                                 const int ntiles, const int32_t* __restrict__ tile_order,
+                                                 const int32_t* __restrict__ tile_node, const int32_t* __restrict__ extptr,
+                                                 const int32_t* __restrict__ rowptr) {
+  TileMeta m;
+  m.t = wid + round_of<GHOST>(kk, nrounds) * nwork;
+  if (m.t >= ntiles) { m.t = -1; m.n0 = m.nrows = m.e0 = m.ne = m.start = m.cnt = 0; return m; }
+  const int tile = GHOST ? tile_order[m.t] : m.t;
+  m.n0 = tile_node[tile];
+  m.nrows = tile_node[tile + 1] - m.n0;
+  m.e0 = extptr[tile];
+  m.ne = extptr[tile + 1] - m.e0;
+  m.start = rowptr[m.n0];
+  m.cnt = rowptr[m.n0 + m.nrows] - m.start;
+  return m;
+}
+
+// all threads of the CTA; smeta: kMetaRounds entries of shared memory; followed by a __syncthreads() of the caller
+template <bool GHOST>
+__device__ __forceinline__ void fetch_tile_meta(TileMeta* smeta, const int nrounds, const int wid, const int nwork,
+                                                const int ntiles, const int32_t* __restrict__ tile_order,
+                                                const int32_t* __restrict__ tile_node, const int32_t* __restrict__ extptr,
+                                                const int32_t* __restrict__ rowptr) {
+  if (nrounds <= kMetaRounds && (int)threadIdx.x < nrounds)
+    smeta[threadIdx.x] = tile_meta_of<GHOST>(threadIdx.x, nrounds, wid, nwork, ntiles, tile_order, tile_node, extptr, rowptr);
+}
+
 struct CellGeom {
   double gx[3], gy[3];  // gradients of the three P1 basis functions
   double area;

@@ -381,18 +381,16 @@ k_tile_t16(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ ti
   bool waited = false, synced = false;
   const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;  // mbox_shifted[col] == mailbox[col - no]
   if (bid >= ntiles) { pdl_wait(); pdl_launch(); }
-  // GHOST: the last round of tile_order holds the tiles with ghost columns; it is visited in the middle so the halo
-  // values pushed at the start of the kernel have arrived and any remaining wait is followed by more work
+  // the CTA's tile schedule, resolved once (mesh tables only: overlaps the previous kernel's drain)
+  __shared__ TileMeta smeta[kMetaRounds];
   const int nrounds = (ntiles + nblk - 1) / nblk;
-  const int mid = nrounds / 2;
+  fetch_tile_meta<GHOST>(smeta, nrounds, bid, nblk, ntiles, tile_order, tile_node, extptr, rowptr);
+  __syncthreads();
   for (int kk = 0; kk < nrounds; ++kk) {
-    const int k = (!GHOST || nrounds < 3) ? kk : (kk == mid ? nrounds - 1 : (kk > mid ? kk - 1 : kk));
-    const int t = bid + k * nblk;
-    if (t >= ntiles) continue;
-    const int tile = GHOST ? tile_order[t] : t;
-    const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
-    const int e0 = extptr[tile], ne = extptr[tile + 1] - e0;
-    const int start = rowptr[n0], cnt = rowptr[n0 + nrows] - start;
+    const TileMeta tm = nrounds <= kMetaRounds ? smeta[kk]
+                                               : tile_meta_of<GHOST>(kk, nrounds, bid, nblk, ntiles, tile_order, tile_node, extptr, rowptr);
+    if (tm.t < 0) continue;
+    const int t = tm.t, n0 = tm.n0, nrows = tm.nrows, e0 = tm.e0, ne = tm.ne, start = tm.start, cnt = tm.cnt;
     for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i] - start;
     const double* __restrict__ v = vals + start;
     const uint16_t* __restrict__ lc = lc16 + start;
@@ -1151,7 +1149,8 @@ static SolveResult bicgstab_5k(cfem_ctx* c, const Matrix& A, const double* b, do
     }
   }
   if (!res.converged) { poll_done(c, res); }
-  halo_exchange(c, x, 1);
+  // the ghost entries of x are NOT refreshed: the callers use the owned part (a Newton update, an exported result)
+  // or exchange the vector they form from it
   if (predict) *predict = res.iters > 0 ? res.iters : 1;
   return res;
 }
@@ -1291,7 +1290,8 @@ static SolveResult bicgstab_merged(cfem_ctx* c, const Matrix& A, const double* b
     }
   }
   if (!res.converged) poll_done(c, res);
-  halo_exchange(c, x, 1);
+  // the ghost entries of x are NOT refreshed: the callers use the owned part (a Newton update, an exported result)
+  // or exchange the vector they form from it
   if (predict) *predict = res.iters > 0 ? res.iters : 1;
   return res;
 }
@@ -1312,7 +1312,8 @@ static SolveResult bicgstab_persist(cfem_ctx* c, const Matrix& A, const double* 
     launch_bicg_persist(c, A, rhat, x, r, p, v, t, rtol2, atol2, max_it); }
   poll_done(c, res);
   persist_comm_advance(c, 2 * (int64_t)res.iters, 3 * (int64_t)res.iters);
-  halo_exchange(c, x, 1);
+  // the ghost entries of x are NOT refreshed: the callers use the owned part (a Newton update, an exported result)
+  // or exchange the vector they form from it
   if (predict) *predict = res.iters > 0 ? res.iters : 1;
   return res;
 }

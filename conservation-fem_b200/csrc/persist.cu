@@ -140,23 +140,12 @@ __device__ __forceinline__ void grid_reduce(const BicgArgs& a, const int nblk, c
   }
 }
 
-// Order in which a CTA visits its rounds (round k = tile wid + k * nwork of tile_order).  tile_order keeps the tiles
-// with ghost columns at the end, i.e. in the last round; visiting that round in the MIDDLE gives the neighbours'
-// halo values (pushed at the start of the phase) time to arrive, and whatever wait remains is followed by more work
-// of the same CTA instead of falling on the barrier.  One GPU: plain order.
-template <bool GHOST>
-__device__ __forceinline__ int round_of(const int kk, const int nrounds) {
-  if (!GHOST || nrounds < 3) return kk;
-  const int mid = nrounds / 2;
-  return kk == mid ? nrounds - 1 : (kk > mid ? kk - 1 : kk);
-}
-
 // One SpMV-type phase over this CTA's tiles.  MODE 0: x = p, y = v, acc[0] += rhat.y.  MODE 1: x = r - alpha v,
 // y = t, acc = {(t,s), (t,t), (rhat,t), (rhat,s)}.
 template <int MODE, bool GHOST>
 __device__ __forceinline__ void spmv_phase(const BicgArgs& a, const int wid, const int nwork, const double alpha,
                                            const unsigned long long hseq, double* prod, double* xs, int32_t* rp,
-                                           double* acc) {
+                                           const TileMeta* smeta, double* acc) {
   const int tid = threadIdx.x;
   const int64_t no = a.no;
   // low-latency halo words of this exchange (p2p.cuh): ghost g in ll[2g], ll[2g+1], polled by the reader
@@ -165,12 +154,10 @@ __device__ __forceinline__ void spmv_phase(const BicgArgs& a, const int wid, con
   const unsigned int tag = (unsigned int)hseq;
   const int nrounds = (a.ntiles + nwork - 1) / nwork;
   for (int kk = 0; kk < nrounds; ++kk) {
-    const int t = wid + round_of<GHOST>(kk, nrounds) * nwork;
-    if (t >= a.ntiles) continue;
-    const int tile = GHOST ? a.tile_order[t] : t;
-    const int n0 = a.tile_node[tile], nrows = a.tile_node[tile + 1] - n0;
-    const int e0 = a.tile_extptr[tile], ne = a.tile_extptr[tile + 1] - e0;
-    const int start = a.rowptr[n0], cnt = a.rowptr[n0 + nrows] - start;
+    const TileMeta tm = nrounds <= kMetaRounds ? smeta[kk]
+                                               : tile_meta_of<GHOST>(kk, nrounds, wid, nwork, a.ntiles, a.tile_order, a.tile_node, a.tile_extptr, a.rowptr);
+    if (tm.t < 0) continue;
+    const int n0 = tm.n0, nrows = tm.nrows, e0 = tm.e0, ne = tm.ne, start = tm.start, cnt = tm.cnt;
     for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = a.rowptr[n0 + i] - start;
     const double* __restrict__ v = a.vals + start;
     const uint16_t* __restrict__ lc = a.lc16 + start;
@@ -195,7 +182,7 @@ __device__ __forceinline__ void spmv_phase(const BicgArgs& a, const int wid, con
       if (GHOST && cc >= no) {
         const long long t0 = clock64();
         val = ll_load(ll + 2 * (size_t)(cc - no), tag, a.error);
-        if (a.tim) {
+        if (a.tim && e == ne - 1) {   // one sample per boundary tile (its last external column is a ghost)
           const unsigned long long dt = (unsigned long long)(clock64() - t0);
           atomicAdd(a.tim + 0, dt);
           atomicAdd(a.tim + 1, 1ull);
@@ -250,6 +237,11 @@ k_bicg_persist(const BicgArgs a) {
   unsigned int gen = 0;
   unsigned long long hseq = a.halo_seq0, rseq = a.red_seq0;
   if (__ldcg(a.status) != 0) return;                    // the initial residual already met the tolerance (uniform)
+  // this CTA's tile schedule: resolved once per solve, used by every phase of every iteration
+  __shared__ TileMeta smeta[kMetaRounds];
+  const int nrounds = comm_cta ? 0 : (a.ntiles + nwork - 1) / nwork;
+  fetch_tile_meta<GHOST>(smeta, nrounds, wid, nwork, a.ntiles, a.tile_order, a.tile_node, a.tile_extptr, a.rowptr);
+  __syncthreads();
   double rho = __ldcg(a.scalars + PS_RHO0);
   const double bb = __ldcg(a.scalars + PS_BB);
   double* const out = a.scalars + PS_D0;
@@ -265,7 +257,7 @@ k_bicg_persist(const BicgArgs a) {
       const double* p = a.p;
       if (a.dev) push_ll(a.dev, hseq, [p](int node) { return __ldcg(p + node); });
     } else {
-      spmv_phase<0, GHOST>(a, wid, nwork, 0.0, hseq, prod, xs, rp, acc);
+      spmv_phase<0, GHOST>(a, wid, nwork, 0.0, hseq, prod, xs, rp, smeta, acc);
       const double s0 = block_sum(acc[0], red);
       if (tid == 0) pPQ[wid] = s0;
     }
@@ -283,7 +275,7 @@ k_bicg_persist(const BicgArgs a) {
       if (a.dev) push_ll(a.dev, hseq, [r, v, alpha](int node) { return __ldcg(r + node) - alpha * __ldcg(v + node); });
     } else {
       acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
-      spmv_phase<1, GHOST>(a, wid, nwork, alpha, hseq, prod, xs, rp, acc);
+      spmv_phase<1, GHOST>(a, wid, nwork, alpha, hseq, prod, xs, rp, smeta, acc);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const double sk = block_sum(acc[k], red);
@@ -305,9 +297,11 @@ k_bicg_persist(const BicgArgs a) {
     // ------------------------------------------------ P4: x, r, p on this CTA's rows
     double rr = 0.0;
     if (!comm_cta) {
-      for (int t = wid; t < a.ntiles; t += nwork) {
-        const int tile = GHOST ? a.tile_order[t] : t;
-        const int n0 = a.tile_node[tile], nrows = a.tile_node[tile + 1] - n0;
+      for (int kk = 0; kk < nrounds; ++kk) {
+        const TileMeta tm = nrounds <= kMetaRounds ? smeta[kk]
+                                                   : tile_meta_of<GHOST>(kk, nrounds, wid, nwork, a.ntiles, a.tile_order, a.tile_node, a.tile_extptr, a.rowptr);
+        if (tm.t < 0) continue;
+        const int n0 = tm.n0, nrows = tm.nrows;
         if (tid < nrows) {
           const int row = n0 + tid;
           const double vi = __ldcg(a.v + row), pi = __ldcg(a.p + row), ti = __ldcg(a.t + row);
@@ -436,12 +430,9 @@ k_cheb_persist(const ChebArgs a) {
       const unsigned int tag = (unsigned int)hseq;
       const int nrounds = (a.ntiles + nwork - 1) / nwork;
       for (int kk = 0; kk < nrounds; ++kk) {
-        const int t = wid + round_of<GHOST>(kk, nrounds) * nwork;
-        if (t >= a.ntiles) continue;
-        const int tile = GHOST ? a.tile_order[t] : t;
-        const int n0 = a.tile_node[tile], nrows = a.tile_node[tile + 1] - n0;
-        const int e0 = a.tile_extptr[tile], ne = a.tile_extptr[tile + 1] - e0;
-        const int start = a.rowptr[n0], cnt = a.rowptr[n0 + nrows] - start;
+        const TileMeta tm = tile_meta_of<GHOST>(kk, nrounds, wid, nwork, a.ntiles, a.tile_order, a.tile_node, a.tile_extptr, a.rowptr);
+        if (tm.t < 0) continue;
+        const int n0 = tm.n0, nrows = tm.nrows, e0 = tm.e0, ne = tm.ne, start = tm.start, cnt = tm.cnt;
         for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = a.rowptr[n0 + i] - start;
         const double* __restrict__ v = a.vals + start;
         const uint16_t* __restrict__ lc = a.lc16 + start;

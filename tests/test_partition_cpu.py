@@ -55,13 +55,50 @@ def test_partition_consistency_random_meshes():
     run()
 
 
-def check_partition(x, c, world):
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("mesh", ["rect", "jittered"])
+def test_partition_consistency_metis(world, mesh):
+    """The same consistency contract with the METIS k-way partition of the nodal graph (node_part from
+    cfem_host_partition): parts become contiguous ranges of the internal order, everything downstream is shared."""
+    x, c = meshes.rectangle(24, 17) if mesh == "rect" else meshes.jittered(21, 19)
+    part = L.host_partition(x, c, world, "metis")
+    assert part.min() == 0 and part.max() == world - 1
+    assert np.array_equal(part, L.host_partition(x, c, world, "metis"))   # deterministic (fixed seed)
+    parts = check_partition(x, c, world, node_part=part)
+    for r, p in enumerate(parts):                                          # rank r owns exactly METIS part r
+        assert np.array_equal(np.sort(p["n2u"][: p["n_owned"]]), np.flatnonzero(part == r))
+    # the Hilbert-range partition written as a node_part array gives the default analysis back, array for array
+    hp = L.host_partition(x, c, world, "hilbert")
+    for r in range(world):
+        a, b = L.host_analyse(x, c, rank=r, world=world), L.host_analyse(x, c, rank=r, world=world, node_part=hp)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+
+
+def test_metis_halo_is_smaller_than_hilbert_ranges_on_the_kpp_mesh():
+    """What the graph partition buys on the jittered KPP mesh (numbers for DESIGN.md section 5 come from the same
+    code at 1448^2): fewer ghost values per rank and no more neighbours than the curve ranges."""
+    x, c = meshes.jittered(160, 160, (-2.0, -2.0), (2.0, 2.0))
+    world = 8
+    part = L.host_partition(x, c, world, "metis")
+    ghosts = {"hilbert": [], "metis": []}
+    for name, npart in (("hilbert", None), ("metis", part)):
+        for r in range(world):
+            p = L.host_analyse(x, c, rank=r, world=world, node_part=npart)
+            ghosts[name].append(p["n_local"] - p["n_owned"])
+    assert sum(ghosts["metis"]) < sum(ghosts["hilbert"])
+    counts = np.bincount(part, minlength=world)
+    assert counts.max() <= 1.04 * counts.mean()                            # METIS load balance (ufactor 1.03)
+
+
+def check_partition(x, c, world, node_part=None):
     nn = x.shape[0]
-    parts = [L.host_analyse(x, c, rank=r, world=world) for r in range(world)]
+    parts = [L.host_analyse(x, c, rank=r, world=world, node_part=node_part) for r in range(world)]
     owned = [p["n2u"][: p["n_owned"]] for p in parts]
     allowned = np.concatenate(owned)
     assert np.array_equal(np.sort(allowned), np.arange(nn))            # a partition of the dofs
-    assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1  # balanced
+    if node_part is None:
+        assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1  # balanced
     ncell_sum = sum(p["n_cells"] for p in parts)
     assert ncell_sum >= c.shape[0] and (world > 1 or ncell_sum == c.shape[0])
     M = p1.mass_matrix(x, c)
@@ -86,6 +123,7 @@ def check_partition(x, c, world):
         bnd[p1.boundary_nodes(c, nn)] = True
         assert np.array_equal(p["is_bnd"].astype(bool), bnd[p["n2u"]])
         assert np.array_equal(p["bnd_user"], p1.boundary_nodes(c, nn))
+    return parts
 
 
 def _free_port():
