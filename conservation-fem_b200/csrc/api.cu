@@ -503,6 +503,7 @@ int cfem_nodal_h(cfem_ctx* c, double* h_out, double rtol, int max_it, int* iters
   if (iters) *iters = r.iters;
   if (h_out) export_vec(c, c->h, h_out);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   if (!r.converged) CFEM_THROW(-3, "nodal_h: PCG did not converge");
   API_END
 }
@@ -526,6 +527,7 @@ int cfem_rv_residual(cfem_ctx* c, int flux, int scheme, double dt, const double*
   if (iters) *iters = r.iters;
   export_vec(c, c->RH, R_io);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   if (!r.converged) CFEM_THROW(-3, "rv_residual: PCG did not converge");
   API_END
 }
@@ -545,6 +547,7 @@ int cfem_rv_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
   export_vec(c, c->eps, eps_out);
   if (variant == CFEM_EPS_LINEAR_SIMPLE && Rh) export_vec(c, c->RH, Rh);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
@@ -566,6 +569,7 @@ int cfem_si_epsilon(cfem_ctx* c, int flux, double Cm, double floor_, int use_bc,
   export_vec(c, c->eps, eps_out);
   if (psi_out) export_vec(c, c->wk[9], psi_out);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
@@ -581,6 +585,7 @@ int cfem_assemble_advection(cfem_ctx* c, double dt, const double* w, const doubl
   launch_adv_system(c, dt, c->w, eps ? c->eps : nullptr, c->u_n, c->g, c->mat[CFEM_MAT_SYSTEM], c->wk[8]);
   if (b_out) export_vec(c, c->wk[8], b_out);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
@@ -596,6 +601,7 @@ int cfem_assemble_cn_residual(cfem_ctx* c, int flux, double dt, const double* uh
   launch_cn_residual(c, flux, dt, c->uh, c->u_n, c->eps, c->g, nullptr, c->wk[8], nullptr);
   export_vec(c, c->wk[8], F_out);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
@@ -607,6 +613,7 @@ int cfem_assemble_cn_jacobian(cfem_ctx* c, int flux, double dt, const double* uh
   import_vec(c, eps, c->eps);
   launch_cn_jacobian(c, flux, dt, c->uh, c->eps, c->mat[CFEM_MAT_SYSTEM]);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
@@ -616,6 +623,7 @@ int cfem_assemble_stiffness(cfem_ctx* c, const double* eps) {
   if (eps) import_vec(c, eps, c->eps);
   launch_stiffness(c, c->mat[CFEM_MAT_STIFFNESS], eps ? c->eps : nullptr);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
@@ -640,6 +648,7 @@ int cfem_spmv(cfem_ctx* c, int which, const double* x, double* y) {
   launch_spmv(c, A, c->wk[8], c->wk[9]);
   export_vec(c, c->wk[9], y);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
@@ -656,6 +665,7 @@ int cfem_solve(cfem_ctx* c, int which, int solver, const double* b, double* x_io
   if (relres) *relres = r.relres;
   export_vec(c, c->wk[9], x_io);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   if (!r.converged) CFEM_THROW(-3, "solve: Krylov solver did not converge");
   API_END
 }
@@ -682,6 +692,7 @@ int cfem_state_set(cfem_ctx* c, const double* uh, const double* u_n, const doubl
   c->krylov_predict = 8;
   c->dx_guess_valid = false;
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
@@ -704,6 +715,7 @@ int cfem_state_get(cfem_ctx* c, double* uh, double* u_n, double* u_old, double* 
   if (eps) export_vec(c, c->eps, eps);
   if (t) *t = c->t;
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
@@ -731,19 +743,43 @@ int cfem_state_get_owned(cfem_ctx* c, double* uh, double* u_n, double* u_old, do
     if (dst[k]) CUDA_OK(cudaMemcpyAsync(dst[k], src[k], c->dm.no * sizeof(double), cudaMemcpyDefault, c->stream));
   if (t) *t = c->t;
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
-// sqrt(sum of the per-CTA partials) on the host (one sync)
+// ||F||_2 of the last residual assembly on the host (one sync).  With in-kernel reductions the assembly kernel has
+// already finished the sum (over its CTAs and, distributed, the ranks) into scalars[24]; otherwise (NCCL fallback) the
+// per-CTA partials are all-reduced and added up here.
 static double partials_norm(cfem_ctx* c, double* part, int npart) {
-  npart = allreduce_sum1(c, part, npart);
   double* tmp = c->h_pinned + 64;
+  if (fin_available(c)) {
+    CUDA_OK(cudaMemcpyAsync(tmp, c->scalars + 24, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return sqrt(tmp[0]);
+  }
+  npart = allreduce_sum1(c, part, npart);
   CUDA_OK(cudaMemcpyAsync(tmp, part, npart * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   double s = 0.0;
   for (int i = 0; i < npart; ++i) s += tmp[i];
   return sqrt(s);
 }
+
+// CUDA event pair that is destroyed on every exit path (a throwing solver must not leak events)
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventPair() { CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b)); }
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  EventPair(const EventPair&) = delete;
+  EventPair& operator=(const EventPair&) = delete;
+};
+// restores the simulation time when a stepper leaves by an exception: the fields of the failed step are undefined
+// (documented in the header), but a caller that reloads the state and retries starts from a consistent clock
+struct TimeGuard {
+  cfem_ctx* c; double t0; bool armed = true;
+  explicit TimeGuard(cfem_ctx* c_) : c(c_), t0(c_->t) {}
+  ~TimeGuard() { if (armed) c->t = t0; }
+};
 
 // smoothness-indicator variant of the scalar stepper (Exact_Burger_SI.py:159-197): SI viscosity instead of the
 // residual projection + RV formula, optional smooth_vector post-filter after the Newton solve
@@ -759,9 +795,9 @@ static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps,
   const int64_t nn = c->dm.nn;
   const Launches l0 = c->launches;
   cfem_step_stats st{};
-  cudaEvent_t ev0, ev1;
-  CUDA_OK(cudaEventCreate(&ev0));
-  CUDA_OK(cudaEventCreate(&ev1));
+  EventPair ev;
+  TimeGuard tguard(c);
+  cudaEvent_t ev0 = ev.a, ev1 = ev.b;
   CUDA_OK(cudaEventRecord(ev0, c->stream));
   const double* d_bc_user = nullptr;
   if (p->bc_kind == CFEM_BC_USER) {
@@ -851,9 +887,8 @@ static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps,
   CUDA_OK(cudaEventSynchronize(ev1));
   comm_check(c);
   { float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); st.device_ms = ms; }
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  tguard.armed = false;
   st.time = c->t;
   st.kernel_launches = c->launches.total - l0.total;
   st.spmv_launches = c->launches.spmv - l0.spmv;
@@ -882,6 +917,7 @@ int cfem_smooth_vector(cfem_ctx* c, double* u_io, const int32_t* order, double l
   launch_smooth_vector(c, u, order, l);
   export_vec(c, u, u_io);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  comm_check(c);   // a timed-out peer exchange must not return garbage with status 0
   API_END
 }
 
@@ -894,9 +930,9 @@ int cfem_step_advection(cfem_ctx* c, const cfem_step_params* p, int n_steps, int
   const int64_t nn = c->dm.nn;
   const Launches l0 = c->launches;
   cfem_step_stats st{};
-  cudaEvent_t ev0, ev1;
-  CUDA_OK(cudaEventCreate(&ev0));
-  CUDA_OK(cudaEventCreate(&ev1));
+  EventPair ev;
+  TimeGuard tguard(c);
+  cudaEvent_t ev0 = ev.a, ev1 = ev.b;
   CUDA_OK(cudaEventRecord(ev0, c->stream));
   const double mass_rtol = p->mass_rtol > 0.0 ? p->mass_rtol : p->lin_rtol;
   double* b = c->wk[8];
@@ -935,9 +971,8 @@ int cfem_step_advection(cfem_ctx* c, const cfem_step_params* p, int n_steps, int
   CUDA_OK(cudaEventSynchronize(ev1));
   comm_check(c);
   { float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); st.device_ms = ms; }
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  tguard.armed = false;
   st.time = c->t;
   st.kernel_launches = c->launches.total - l0.total;
   st.spmv_launches = c->launches.spmv - l0.spmv;
@@ -1052,17 +1087,16 @@ int cfem_step_euler(cfem_ctx* c, const cfem_step_params* p, int n_steps, cfem_st
   if (!(p->dt > 0.0)) CFEM_THROW(-1, "step_euler: dt must be positive");
   const Launches l0 = c->launches;
   cfem_step_stats st{};
-  cudaEvent_t ev0, ev1;
-  CUDA_OK(cudaEventCreate(&ev0));
-  CUDA_OK(cudaEventCreate(&ev1));
+  EventPair ev;
+  TimeGuard tguard(c);
+  cudaEvent_t ev0 = ev.a, ev1 = ev.b;
   CUDA_OK(cudaEventRecord(ev0, c->stream));
   euler_steps(c, p, n_steps, &st);
   CUDA_OK(cudaEventRecord(ev1, c->stream));
   CUDA_OK(cudaEventSynchronize(ev1));
   comm_check(c);
   { float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); st.device_ms = ms; }
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
+  tguard.armed = false;
   st.time = c->t;
   st.kernel_launches = c->launches.total - l0.total;
   st.spmv_launches = c->launches.spmv - l0.spmv;
@@ -1083,9 +1117,8 @@ int cfem_time_kernel(cfem_ctx* c, int kernel, int flux, int reps, double* ms_per
   const double tile_cells = (double)c->dm.nc * 1.0;  // lower bound: every cell staged once
   const double meta = 16.0 * tile_cells + 4.0 * 3.0 * nc + 8.0 * nn + 16.0 * nn;
   double bytes = 0.0;
-  cudaEvent_t e0, e1;
-  CUDA_OK(cudaEventCreate(&e0));
-  CUDA_OK(cudaEventCreate(&e1));
+  EventPair evp;
+  cudaEvent_t e0 = evp.a, e1 = evp.b;
   Matrix& M = c->mat[CFEM_MAT_MASS_BC];
   Matrix& J = c->mat[CFEM_MAT_SYSTEM];
   auto body = [&]() {
@@ -1125,8 +1158,6 @@ int cfem_time_kernel(cfem_ctx* c, int kernel, int flux, int reps, double* ms_per
   CUDA_OK(cudaEventSynchronize(e1));
   float ms = 0.f;
   CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (ms_per_launch) *ms_per_launch = (double)ms / reps;
   if (algorithmic_bytes) *algorithmic_bytes = bytes;
   API_END

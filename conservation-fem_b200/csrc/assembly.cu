@@ -15,6 +15,7 @@
 // Code/KPP/KPP_exact.py:123-154, Code/Utils/helpers.py:29-36).
 #include "device_utils.cuh"
 #include "launch.h"
+#include "p2p.cuh"
 
 #ifndef CFEM_RES_PREFETCH
 #define CFEM_RES_PREFETCH true    // A/B switch of the residual op's phase-A prefetch (see k_tile_assemble)
@@ -394,7 +395,8 @@ static_assert(kTileCellCap <= 3 * kTileNodes, "phase A visits at most three cell
 template <class Op>
 __global__ void __launch_bounds__(kTileNodes, Op::MINB)
 k_tile_assemble(const DevMesh m, const Op op, const bool bc, double* __restrict__ vals,
-                double* __restrict__ dinv, double* __restrict__ partials, const int ccap, const int nnzcap) {
+                double* __restrict__ dinv, double* __restrict__ partials, const int ccap, const int nnzcap,
+                const Fin fin, double* __restrict__ fin_out) {
   pdl_wait();
   pdl_launch();
   constexpr int NV = Op::NV;
@@ -502,6 +504,12 @@ k_tile_assemble(const DevMesh m, const Op op, const bool bc, double* __restrict_
   if (partials) {
     const double s = block_sum(local, red);
     if (tid == 0) partials[blockIdx.x] = s;
+    if (fin.counter) {   // total (over the CTAs and, distributed, the ranks) finished here: the host reads ONE scalar
+      __shared__ double sums[1];
+      Slots<1> sl;
+      sl.p[0] = partials;
+      if (fin_reduce<1>(fin, sl, gridDim.x, red, sums) && tid == 0) fin_out[0] = sums[0];
+    }
   }
 }
 
@@ -516,19 +524,28 @@ template <class Op>
 static int run_tiles(cfem_ctx* c, const Op& op, bool bc, double* vals, double* dinv, double* partials) {
   const int ccap = c->hm.max_tile_cells, nnzcap = c->hm.max_tile_nnz;
   const size_t smem = sizeof(double) * ((size_t)Op::NV * 3 * ccap + (Op::MAT ? (size_t)9 * ccap + nnzcap : 0));
-  static int occ = 0;  // per template instantiation (one mesh capacity per process is the common case)
-  static size_t occ_smem = 0;
-  if (occ == 0 || occ_smem != smem) {
-    CUDA_OK(cudaFuncSetAttribute(k_tile_assemble<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile_assemble<Op>, kTileNodes, smem));
-    if (occ < 1) CFEM_THROW(-2, "assembly kernel does not fit on an SM");
-    occ_smem = smem;
+  // occupancy per (instantiation, context): the answer depends on the tile capacities of THIS mesh and on the device
+  // of THIS context, so it is cached in the context (keyed by the kernel's address), not in a function static
+  int occ = 0;
+  {
+    const void* key = (const void*)k_tile_assemble<Op>;
+    for (auto& e : c->asm_occ)
+      if (e.first == key) { occ = e.second; break; }
+    if (occ == 0) {
+      CUDA_OK(cudaFuncSetAttribute(k_tile_assemble<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile_assemble<Op>, kTileNodes, smem));
+      if (occ < 1) CFEM_THROW(-2, "assembly kernel does not fit on an SM");
+      c->asm_occ.emplace_back(key, occ);
+    }
   }
   int grid = c->sm_count * occ;
   if (grid > c->dm.ntiles) grid = c->dm.ntiles;
   if (grid > kMaxPartials) grid = kMaxPartials;
   ProfScope ps(c, Op::MAT ? PROF_ASM_MAT : PROF_ASM_VEC);
-  launch_pdl(k_tile_assemble<Op>, grid, kTileNodes, smem, c->stream, c->dm, op, bc, vals, dinv, partials, ccap, nnzcap);
+  // a kernel that produces partials also finishes their sum when in-kernel reductions are available (scalars[24])
+  const bool finish = partials != nullptr && fin_available(c);
+  launch_pdl(k_tile_assemble<Op>, grid, kTileNodes, smem, c->stream, c->dm, op, bc, vals, dinv, partials, ccap, nnzcap,
+             finish ? make_fin(c) : Fin(), c->scalars + 24);
   CUDA_OK(cudaGetLastError());
   c->launches.total++;
   c->launches.assembly++;

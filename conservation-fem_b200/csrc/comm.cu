@@ -10,6 +10,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -419,10 +420,8 @@ static void p2p_setup(cfem_ctx* c) {
   CUDA_OK(cudaMalloc((void**)&pp->d_dev, sizeof(P2PDev)));
   CUDA_OK(cudaMemcpy(pp->d_dev, &d, sizeof(P2PDev), cudaMemcpyHostToDevice));
   c->allocs.push_back(pp->d_dev);
-  // every rank must have its mailbox mapped everywhere before the first exchange: one tiny all-reduce
-  double* tmp = c->partials;
-  NCCL_OK(nccl().AllReduce(tmp, tmp, 1, ncclDouble, ncclSum, comm, c->stream));
-  CUDA_OK(cudaStreamSynchronize(c->stream));
+  // every rank must have its mailbox mapped everywhere before the first exchange: the agreement all-reduce in
+  // comm_setup_exchange is that barrier (kept out of here so that a rank failing above still takes part in it)
   c->p2p = pp;
 }
 
@@ -442,7 +441,30 @@ void comm_setup_exchange(cfem_ctx* c) {
   if (c->world == 1) return;
   const char* e = getenv("CFEM_COMM");
   if (e && std::string(e) == "nccl") return;
-  p2p_setup(c);
+  // Peer memory needs CUDA IPC between all ranks (one node, peer access).  Where a rank cannot set it up, ALL ranks
+  // must fall back to the NCCL data plane together: the verdict is agreed with a MIN all-reduce.
+  int ok = 1;
+  std::string why;
+  try {
+    p2p_setup(c);
+  } catch (const Error& err) {
+    ok = 0;
+    why = err.msg;
+    cudaGetLastError();
+  }
+  int* dflag = nullptr;
+  CUDA_OK(cudaMalloc((void**)&dflag, sizeof(int)));
+  CUDA_OK(cudaMemcpy(dflag, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  NCCL_OK(nccl().AllReduce(dflag, dflag, 1, ncclInt, ncclMin, comm, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  int all_ok = 0;
+  CUDA_OK(cudaMemcpy(&all_ok, dflag, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(dflag);
+  if (!all_ok) {
+    comm_destroy_p2p(c);   // a rank that did succeed lets go of its mappings again
+    if (!ok) fprintf(stderr, "cfem_b200: rank %d: peer-memory exchange unavailable (%s); all ranks use the NCCL path\n", c->rank, why.c_str());
+  }
 }
 
 void comm_check(cfem_ctx* c) {

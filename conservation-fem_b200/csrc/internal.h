@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/cfem_b200.h"
@@ -200,6 +201,7 @@ struct cfem_ctx {
   size_t hot_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // MASS_BC vals | rowptr | lc16 | extptr | ext | SYSTEM vals | colidx | end
   size_t l2_setaside = 0;                // bytes of L2 set aside for persisting lines (0: feature off)
   size_t l2_max_window = 0;
+  std::vector<std::pair<const void*, int>> asm_occ;   // occupancy of the assembly kernel instantiations on this context
   void* persist_plan = nullptr;          // launch plan of the persistent BiCGStab kernel (persist.cu)
   int t16_grid = 0;                      // grid of the T16 tile kernels (occupancy x SMs, <= tiles), 0 = not sized yet
   int l2_window = 0;                     // matrix id whose window is currently attached to the stream, -1 none

@@ -353,7 +353,14 @@ struct Ep16Cheb {  // one Chebyshev iteration of the mass solve: r = b - M x, z 
     if (FIRST) sl.p[NACC - 1] = p1;
     return sl;
   }
-  __device__ __forceinline__ void finish(const double*) const {}
+  // finished norms (Fin): scalars[S_D0] = ||D^-1 r||^2 of this launch, scalars[S_D0 + 1] = ||D^-1 b||^2 (first launch)
+  double* out;
+  __device__ __forceinline__ void finish(const double* sums) const {
+    if (out && threadIdx.x == 0) {
+      out[0] = sums[0];
+      if (FIRST) out[1] = sums[NACC - 1];
+    }
+  }
 };
 
 template <class EP, bool GHOST>
@@ -653,6 +660,9 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
   if (target < 2) target = 2;
   if (target > max_it) target = max_it;
   const bool persist = use_t16() && cheb_persist_available(c);
+  const bool fin_norms = use_t16() && fin_available(c) && !persist;   // norms finished inside the first / last launch
+  bool first_chunk = true;
+  double bb2 = 0.0;
   while (true) {
     if (persist) {
       // all iterations up to the next check in ONE cooperative launch (persist.cu); the scope stands for
@@ -683,10 +693,13 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
              c->dm.tile_order, c->dm.n_interior, c->dm.ntiles, c->dm.tile_node, c->dm.rowptr, c->dm.colidx, A.vals, A.dinv, \
              b, xa, xb, d, C1, C2, part + P_RR * kMaxPartials, PBB)
       if (use_t16() && it == 0) {
-        launch_t16(c, gsrc, A, xa, Ep16Cheb<true>{A.dinv, b, xb, d, 0.0, 1.0 / theta, part + P_RR * kMaxPartials, part + P_BB * kMaxPartials}, false);
+        // the first launch finishes ||D^-1 b||^2, the last one of the chunk ||D^-1 r||^2 (in-kernel, all ranks)
+        launch_t16(c, gsrc, A, xa, Ep16Cheb<true>{A.dinv, b, xb, d, 0.0, 1.0 / theta, part + P_RR * kMaxPartials, part + P_BB * kMaxPartials, c->scalars + S_D0},
+                   false, fin_norms ? make_fin(c) : Fin());
       } else if (use_t16()) {
         const double rho_new = 1.0 / (2.0 * sigma1 - rho);
-        launch_t16(c, gsrc, A, xa, Ep16Cheb<false>{A.dinv, b, xb, d, rho_new * rho, 2.0 * rho_new / delta, part + P_RR * kMaxPartials, nullptr}, false);
+        launch_t16(c, gsrc, A, xa, Ep16Cheb<false>{A.dinv, b, xb, d, rho_new * rho, 2.0 * rho_new / delta, part + P_RR * kMaxPartials, nullptr, c->scalars + S_D0},
+                   false, (fin_norms && it == target - 1) ? make_fin(c) : Fin());
         rho = rho_new;
       } else if (it == 0) {
         if (gsrc.mbox) CHEB_LAUNCH(true, true, 0.0, 1.0 / theta, part + P_BB * kMaxPartials);
@@ -700,15 +713,24 @@ SolveResult chebyshev_mass(cfem_ctx* c, const Matrix& A, const double* b, double
 #undef CHEB_LAUNCH
       LAUNCHED(c);
       c->launches.spmv++;
-      if (it == 0) np_bb = allreduce_sum1(c, part + P_BB * kMaxPartials, gs);
+      if (it == 0 && !fin_norms) np_bb = allreduce_sum1(c, part + P_BB * kMaxPartials, gs);
       std::swap(xa, xb);
     }
     }
     // the last kernel measured ||b - M x_{it-1}||; x_it is one update further on
+    if (fin_norms) {
+      // scalars[S_D0] = ||D^-1 r||^2 (last launch), scalars[S_D0 + 1] = ||D^-1 b||^2 (first launch of the solve; kept in bb2)
+      CUDA_OK(cudaMemcpyAsync(c->h_pinned + 8, c->scalars + S_D0, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_OK(cudaStreamSynchronize(c->stream));
+      if (first_chunk) bb2 = c->h_pinned[9];
+      first_chunk = false;
+      c->h_pinned[0] = bb2 > 0.0 ? sqrt(c->h_pinned[8] / bb2) : sqrt(c->h_pinned[8]);
+    } else {
     const int np_rr = allreduce_sum1(c, part + P_RR * kMaxPartials, gs);
     { ProfScope ps(c, PROF_KRYLOV_VEC); launch_pdl(k_relres, 1, kBlock, 0, c->stream, part, np_rr, np_bb, c->scalars); LAUNCHED(c); }
     CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + S_RELRES, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
     }
     res.iters = it;
     res.relres = c->h_pinned[0];
