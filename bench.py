@@ -259,7 +259,9 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=None, help="cells per side (per GPU) of the mesh; default per workload")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=None,
+                    help="cells per side (per GPU) of the mesh; default per workload (use --size under torchrun, whose "
+                         "own parser claims the prefix --n)")
     ap.add_argument("--workload", default="burgers", choices=["burgers", "kpp", "euler"],
                     help="burgers = BASELINE configs[1] (default, the quoted metric); kpp = configs[2] "
                          "(4.2M-cell permuted unstructured mesh); euler = configs[3] (8M cells, 4 components)")

@@ -5,6 +5,7 @@
 namespace cfem {
 
 constexpr int kBlock = 256;  // threads per CTA for every kernel in the library
+constexpr size_t kDynSmemCeiling = 200 * 1024;  // dynamic shared memory every tile kernel is opted in to (sm_100: 227 KB per CTA)
 
 // Programmatic dependent launch (griddepcontrol): a kernel launched with launch_pdl() may become resident while
 // the previous kernel of the stream is still draining.  pdl_wait() blocks until that kernel has completed and

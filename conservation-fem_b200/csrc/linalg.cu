@@ -466,7 +466,11 @@ static size_t t16_smem_bytes(const cfem_ctx* c) { return sizeof(double) * ((size
 template <class EP, bool GHOST>
 static int t16_prepare_one(cfem_ctx* c) {
   const size_t smem = t16_smem_bytes(c);
-  CUDA_OK(cudaFuncSetAttribute(k_tile_t16<EP, GHOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // The opt-in is a property of the FUNCTION, shared by every context of the process: it is raised to a fixed
+  // ceiling, never set to what one mesh needs (a later context with smaller tiles would lower it under the feet
+  // of an earlier one -- "invalid argument" at the next launch of the earlier context).
+  if (smem > kDynSmemCeiling) CFEM_THROW(-2, "T16 tile kernel: a tile has too many external columns for shared memory");
+  CUDA_OK(cudaFuncSetAttribute(k_tile_t16<EP, GHOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemCeiling));
   int occ = 0;
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile_t16<EP, GHOST>, kTileNodes, smem));
   if (occ < 1) CFEM_THROW(-2, "T16 tile kernel does not fit on an SM (too many external columns per tile)");

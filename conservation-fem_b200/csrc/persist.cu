@@ -506,7 +506,9 @@ struct PersistPlan { int grid = 0, grid_cheb = 0; size_t smem = 0; bool ok = fal
 
 template <class K>
 static int plan_kernel(cfem_ctx* c, K kern, size_t smem, bool ghost) {
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  // fixed ceiling, not this mesh's need: the attribute belongs to the function and is shared by all contexts
+  if (smem > kDynSmemCeiling) return 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemCeiling) != cudaSuccess) { cudaGetLastError(); return 0; }
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTileNodes, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return 0; }
   int64_t grid = (int64_t)occ * c->sm_count;

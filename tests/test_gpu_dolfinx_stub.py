@@ -130,3 +130,25 @@ def test_solver_entry_points_take_the_stub_mesh(setup):
     uh = GS.solve_kpp(dom, dt=dt, num_steps=3)
     st, _, _ = S.run_kpp(x, c, dt, 3)
     assert np.linalg.norm(uh.x.array - st.uh) <= 1e-10 * np.linalg.norm(st.uh)
+
+
+def test_contexts_with_different_tile_footprints_coexist():
+    """Kernel attributes (dynamic shared-memory opt-in, occupancy) belong to the function / device, not to one mesh:
+    a context created LATER with smaller tiles must not invalidate the launches of an earlier one (regression: the
+    8-GPU bench died with 'invalid argument' after its small parity contexts had lowered the opt-in)."""
+    from cfem_b200 import _lib as L
+
+    xa, ca = meshes.rectangle(70, 60)
+    xb, cb = meshes.rectangle(9, 8)
+    a = Context((xa, ca), order="natural")      # row-major numbering: ~140 external columns per tile
+    va = np.random.default_rng(0).normal(size=a.n)
+    ya = a.spmv(L.MAT_MASS, va)
+    b = Context((xb, cb))                        # tiny tiles, created afterwards
+    vb = np.ones(b.n)
+    assert abs(b.spmv(L.MAT_MASS, vb).sum() - 1.0) < 1e-13
+    assert np.array_equal(a.spmv(L.MAT_MASS, va), ya)          # the first context still launches, same bits
+    h1 = a.nodal_h()
+    b.close()
+    assert np.array_equal(a.solve(L.MAT_MASS, ya, solver="chebyshev", rtol=1e-13), a.solve(L.MAT_MASS, ya, solver="chebyshev", rtol=1e-13))
+    assert np.all(h1 > 0)
+    a.close()

@@ -124,3 +124,44 @@ def test_degree5_rule_constants(forms):
     assert key(pts, 2.0 * w) == key(B, W)
     for p in pts:   # and as ordered triples, up to the basis-function numbering (1 - x - y, x, y)
         assert any(np.allclose(p, b, atol=1e-14) for b in B)
+
+
+def _table(src, name, rows, cols):
+    m = re.search(name + r"\[1\]\[%d\]\[%d\] =\s*\{ \{(.*?)\} \} \};" % (rows, cols), src, re.S)
+    vals = [float(t) for t in re.findall(r"-?\d+\.\d+(?:[eE][-+]?\d+)?|-?\d+\.(?![\d])|-?\d+(?=[,\s}])", m.group(1))]
+    return np.array(vals).reshape(rows, cols)
+
+
+def test_l2_error_functional_against_p3_interpolant(forms):
+    """``oracle.p3.l2_error_p3`` (closed form e^T M3 e |K|) against the reference's generated kernel for
+    ``L2 = (u0 - u_ex)^2 dx`` with u_ex in P3 (Burger.ufl:40, Burger.cpp:5957-6043, 12-point degree-6 rule).
+
+    The generated code numbers the ten P3 dofs its own way; the permutation is read off its basis-function table
+    (values of the ten functions at the rule's points) instead of being assumed."""
+    from oracle import p3
+
+    src = open(os.path.join(build_ref.OUT_DIR, "burger_tt.cpp")).read()
+    body = src[src.index('extern "C" void burger_tt3('):src.index('extern "C" void burger_tt4(')]
+    P1tab = _table(body, "FE3_C0_Q12", 12, 3)      # P1 basis at the points == barycentric coordinates (l0, l1, l2)
+    P3tab = _table(body, "FE5_C0_Q12", 12, 10)
+    ours = p3.basis(P1tab)                          # our ten functions at the same points
+    perm = []
+    for j in range(10):                             # generated dof j is our dof perm[j]
+        d = np.abs(ours - P3tab[:, [j]]).max(axis=0)
+        assert d.min() < 1e-12, (j, d.min())
+        perm.append(int(d.argmin()))
+    assert sorted(perm) == list(range(10))
+    tris, rng = _triangles(40, seed=21)
+    worst = 0.0
+    for xy in tris:
+        u0 = rng.normal(size=3)
+        ue = rng.normal(size=10)                    # in OUR dof order
+        ref = forms.L2(xy, u0, ue[perm])            # int (u0 - u_ex)^2 over the cell, reference kernel
+        got = p3.l2_error_p3(xy, np.array([[0, 1, 2]]), u0, ue[None, :]) ** 2
+        worst = max(worst, abs(got - ref) / ref)
+    assert worst < 1e-13, worst
+    # a P1 function is its own P3 interpolant: zero error, and a quadratic is reproduced exactly by P3
+    x = np.array([[0.0, 0.0], [1.0, 0.2], [0.3, 0.9]])
+    c = np.array([[0, 1, 2]])
+    lin = lambda p: 2.0 * p[:, 0] - 3.0 * p[:, 1] + 0.5  # noqa: E731
+    assert p3.l2_error_p3(x, c, lin(x), lin) < 1e-15

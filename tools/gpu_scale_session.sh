@@ -26,9 +26,9 @@ for what in "$@"; do
   case $what in
     burgers) run burgers --steps 20 --warmup 3 --no-cpu-baseline ;;
     metis)   run burgers_metis --steps 20 --warmup 3 --sweep --no-parity --partition metis ;;
-    kstrong) run kpp_strong --workload kpp --strong --n 4000 --steps 10 --warmup 3 --sweep --no-parity ;;
-    kstrong_metis) run kpp_strong_metis --workload kpp --strong --n 4000 --steps 10 --warmup 3 --sweep --no-parity --partition metis ;;
-    kweak)   run kpp_weak --workload kpp --n 2828 --steps 10 --warmup 3 --sweep --no-parity ;;
+    kstrong) run kpp_strong --workload kpp --strong --size 4000 --steps 10 --warmup 3 --sweep --no-parity ;;
+    kstrong_metis) run kpp_strong_metis --workload kpp --strong --size 4000 --steps 10 --warmup 3 --sweep --no-parity --partition metis ;;
+    kweak)   run kpp_weak --workload kpp --size 2828 --steps 10 --warmup 3 --sweep --no-parity ;;
     dist)    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 tests/dist_gpu_check.py > gpurun_out/${TAG}_dist.log 2>&1; grep "dist x\|DIST_\|Error" gpurun_out/${TAG}_dist.log | grep -v "comm:" | sort | uniq | head -8 ;;
   esac
 done
