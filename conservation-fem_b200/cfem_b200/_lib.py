@@ -87,6 +87,7 @@ SIGNATURES = {
     "cfem_device_bytes": (_L, [_P]),
     "cfem_device_limits": (_I, [_I, _P]),
     "cfem_comm_timers": (_I, [_P, _P, _I]),
+    "cfem_l2_error_p3": (_I, [_P, _P, _P, _P]),
     "cfem_get_csr_pattern": (_I, [_P, _P, _P]),
     "cfem_get_boundary_dofs": (_I, [_P, _P]),
     "cfem_set_dirichlet": (_I, [_P, _P, _L]),

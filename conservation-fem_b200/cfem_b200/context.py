@@ -371,6 +371,33 @@ class Context:
         L.check(self._lib.cfem_comm_stats(self._h, C.byref(a), C.byref(b), C.byref(d)))
         return {"halo_exchanges": a.value, "allreduces": b.value, "halo_doubles_sent_per_exchange": d.value}
 
+    # -- (f-2) L2 error against the P3 interpolant of an exact solution
+    P3_NODES = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 2 / 3, 1 / 3], [0, 1 / 3, 2 / 3], [2 / 3, 0, 1 / 3],
+                         [1 / 3, 0, 2 / 3], [2 / 3, 1 / 3, 0], [1 / 3, 2 / 3, 0], [1 / 3, 1 / 3, 1 / 3]])
+
+    def p3_cell_points(self):
+        """(Nc, 10, 2) coordinates of the P3 Lagrange nodes of every cell, in the node order ``cfem_l2_error_p3``
+        expects: the cell's 3 vertices, 2 per edge (opposite vertex 0, 1, 2), centroid."""
+        return np.einsum("pk,ckd->cpd", self.P3_NODES, self.x[self.cells][:, :, :2])
+
+    def l2_error_p3(self, uh, exact):
+        """``sqrt(assemble_scalar((uh - u_exact)**2 * dx))`` with ``u_exact = Function(P3).interpolate(exact)``
+        (``Exact_Burger_RV_conv.py:81-86,223``).  ``exact``: callable on ``x`` with shape ``(3, N)`` like
+        ``Function.interpolate``, or a ready ``(Nc, 10)`` table at ``p3_cell_points()``.  ``uh`` None: the resident uh."""
+        if callable(exact):
+            pts = self.p3_cell_points().reshape(-1, 2)
+            X = np.zeros((3, pts.shape[0]))
+            X[0], X[1] = pts[:, 0], pts[:, 1]
+            table = np.asarray(exact(X), dtype=np.float64).reshape(-1, 10)
+        else:
+            table = np.asarray(exact, dtype=np.float64).reshape(-1, 10)
+        if table.shape[0] != self.cells.shape[0]:
+            raise ValueError("exact-solution table must have one row of 10 values per cell")
+        table = np.ascontiguousarray(table)
+        err = C.c_double(0.0)
+        L.check(self._lib.cfem_l2_error_p3(self._h, L.ptr(_field(uh)), L.ptr(table), C.byref(err)))
+        return err.value
+
     def comm_timers(self, reset=True):
         """Device-measured waits of the peer-memory data plane since the last reset (microseconds / counts)."""
         out = (C.c_double * 8)()

@@ -67,6 +67,35 @@ def burgers_initial_condition(x):
     return u
 
 
+def burgers_exact_solution(x, t=0.5):
+    """Exact solution of the 2-D Burgers Riemann problem, ``Code/Burgers_equation/Exact_Burger_RV.py:37-66`` /
+    ``Exact_Burger_RV_conv.py:31-60``; ``x`` has shape ``(3|2, N)`` like ``Function.interpolate`` passes it.
+    (At ``t = 0`` the fan branch divides by zero exactly as the reference's expression does; the NaN comparisons
+    are False and the other branches give the initial data.)"""
+    X, Y = x[0], x[1]
+    u = np.zeros_like(X)
+    with np.errstate(all="ignore"):
+        m1 = X <= (1 / 2 - 3 * t / 5)
+        u = np.where(m1 & (Y > (1 / 2 + 3 * t / 20)), -0.2, u)
+        u = np.where(m1 & (Y <= (1 / 2 + 3 * t / 20)), 0.5, u)
+        m2 = ((1 / 2 - 3 * t / 5) <= X) & (X <= (1 / 2 - t / 4))
+        l2 = -8 * X / 7 + 15 / 14 - 15 * t / 28
+        u = np.where(m2 & (Y > l2), -1, u)
+        u = np.where(m2 & (Y <= l2), 0.5, u)
+        m3 = (1 / 2 - t / 4 <= X) & (X <= (1 / 2 + t / 2))
+        l3 = X / 6 + 5 / 12 - 5 * t / 24
+        u = np.where(m3 & (Y > l3), -1, u)
+        u = np.where(m3 & (Y <= l3), 0.5, u)
+        m4 = (1 / 2 + t / 2 <= X) & (X <= (1 / 2 + 4 * t / 5))
+        l4 = X - 5 / (18 * t) * (X + t - 1 / 2) ** 2 if t != 0 else X - np.float64(5) / np.float64(0.0) * (X + t - 1 / 2) ** 2
+        u = np.where(m4 & (Y > l4), -1, u)
+        u = np.where(m4 & (Y <= l4), (2 * X - 1) / (2 * t) if t != 0 else (2 * X - 1) / np.float64(0.0), u)
+        m5 = X >= (1 / 2 + 4 * t / 5)
+        u = np.where(m5 & (Y > (1 / 2 - t / 10)), -1, u)
+        u = np.where(m5 & (Y <= (1 / 2 - t / 10)), 0.8, u)
+    return u
+
+
 def advection_initial_condition(x, r0=0.25, x0_1=0.3, x0_2=0):
     """``Code/Linear_advection/RV_node.py:54-55``."""
     return 1 / 2 * (1 - np.tanh(((x[0] - x0_1) ** 2 + (x[1] - x0_2) ** 2) / r0 ** 2 - 1))
@@ -83,15 +112,38 @@ def advection_dt(w, hmax, CFL=0.5):
 
 
 # ---- loops ------------------------------------------------------------------------
+def _step_user_bc(ctx, p, num_steps, bc_of_step):
+    """``num_steps`` steps with caller-supplied Dirichlet values: ``bc_of_step(k)`` -> values on ``ctx.boundary_dofs()``
+    for step k (0-based).  The library stages at most 2 N values per call, so the steps go in chunks."""
+    nb = ctx.boundary_dofs().size
+    chunk = max(1, (2 * ctx.n) // max(nb, 1))
+    stats, done = None, 0
+    while done < num_steps:
+        k = min(chunk, num_steps - done)
+        vals = np.ascontiguousarray(np.stack([bc_of_step(done + j) for j in range(k)]), dtype=np.float64)
+        st = ctx.step_scalar(p, k, bc_values=vals)
+        done += k
+        if stats is None:
+            stats = st
+        else:
+            for key in ("steps", "newton_iterations", "krylov_iterations", "mass_iterations", "kernel_launches",
+                        "spmv_launches", "assembly_launches", "device_ms"):
+                stats[key] += st[key]
+            stats["time"], stats["last_newton_residual"] = st["time"], st.get("last_newton_residual")
+    return stats
+
+
 def _run_scalar(flux, domain, u0, dt, num_steps, Cvel, Crv, bc_kind, bc_value, scheme, newton_rtol,
-                solver, lin_rtol, device, h, return_stats, xdmf=None, write_every=1, mass_rtol=0.0):
+                solver, lin_rtol, device, h, return_stats, xdmf=None, write_every=1, mass_rtol=0.0, bc_of_step=None):
     ctx = domain if isinstance(domain, Context) else Context.for_domain(domain, device=device)
     u0 = _interpolate(ctx, u0)
     h = ctx.nodal_h() if h is None else _interpolate(ctx, h)
     ctx.state_set(uh=u0, u_n=u0, u_old=u0, u_oo=u0, RH=np.zeros(ctx.n), h=h, t=0.0)
     p = step_params(flux, dt, Cvel, Crv, scheme=scheme, newton_rtol=newton_rtol, solver=solver,
                     lin_rtol=lin_rtol, bc_kind=bc_kind, bc_value=bc_value, mass_rtol=mass_rtol)
-    if xdmf is None:
+    if bc_of_step is not None:
+        stats = _step_user_bc(ctx, p, num_steps, bc_of_step)
+    elif xdmf is None:
         stats = ctx.step_scalar(p, num_steps)
     else:
         # xdmf.write_mesh(domain); xdmf.write_function(uh, t) every `write_every` steps (KPP_exact.py:108-109,165)
@@ -134,10 +186,13 @@ def solve_kpp(domain, initial_condition=kpp_initial_condition, dt=0.01, num_step
 
 def solve_burgers(domain, initial_condition=burgers_initial_condition, dt=None, num_steps=None, Cvel=0.5,
                   Crv=10.0, CFL=0.5, T=0.5, scheme="bdf2", newton_rtol=1e-4, solver="bicgstab",
-                  lin_rtol=1e-13, device=0, h=None, return_stats=False, xdmf=None, write_every=1, mass_rtol=0.0):
+                  lin_rtol=1e-13, device=0, h=None, return_stats=False, xdmf=None, write_every=1, mass_rtol=0.0,
+                  bc_time_lag=False):
     """2-D inviscid Burgers Riemann problem with exact Dirichlet data (``Exact_Burger_RV.py``).
 
     ``dt=None`` reproduces ``dt = CFL*min(h_CG)``, ``num_steps = ceil(T/dt)`` (``:105-109``).
+    ``scheme="bdf1", bc_time_lag=True`` is the variant of the convergence study ``Exact_Burger_RV_conv.py``
+    (BDF1 residual ``:186``, Dirichlet data one step behind ``:172-177``).
     """
     ctx = domain if isinstance(domain, Context) else Context.for_domain(domain, device=device)
     if dt is None:
@@ -145,6 +200,15 @@ def solve_burgers(domain, initial_condition=burgers_initial_condition, dt=None, 
         dt = CFL * float(np.min(hh))
     if num_steps is None:
         num_steps = int(np.ceil(T / dt))
+    if bc_time_lag:
+        # Exact_Burger_RV_conv.py:172-177 interpolates the exact solution BEFORE it advances t: step k (0-based)
+        # carries the Dirichlet data of time k dt, not (k+1) dt
+        bnd = ctx.boundary_dofs()
+        Xb = np.zeros((3, bnd.size))
+        Xb[0], Xb[1] = ctx.x[bnd, 0], ctx.x[bnd, 1]
+        return _run_scalar(L.FLUX_BURGERS, ctx, initial_condition, dt, num_steps, Cvel, Crv, "user", 0.0, scheme,
+                           newton_rtol, solver, lin_rtol, device, h, return_stats, xdmf, write_every, mass_rtol,
+                           bc_of_step=lambda k: burgers_exact_solution(Xb, k * dt))
     return _run_scalar(L.FLUX_BURGERS, ctx, initial_condition, dt, num_steps, Cvel, Crv, "burgers_exact", 0.0,
                        scheme, newton_rtol, solver, lin_rtol, device, h, return_stats, xdmf, write_every, mass_rtol)
 
@@ -288,13 +352,17 @@ def solve_advection_rk4(domain, initial_condition=advection_initial_condition, v
 
 
 # ---- (f-2) L2-error functional and convergence-rate fit -------------------------------------------------
-def l2_error(domain, uh, u_ref):
-    """``sqrt(assemble_scalar((uh - u_ref)**2 * dx))`` with both fields in P1 (mass-matrix norm on the GPU).
+def l2_error(domain, uh, u_ref, degree=1):
+    """``sqrt(assemble_scalar((uh - u_ref)**2 * dx))``.
 
-    The reference integrates against a P3 interpolant of the exact solution
-    (``Code/Linear_advection/RV_node_convergence.py:49,239``); here ``u_ref`` is its P1 interpolant (nodal values
-    or a callable of ``x`` with shape ``(3, N)``)."""
+    ``degree=3``: ``u_ref`` (a callable of ``x`` with shape ``(3, N)``) is interpolated into P3 like the reference does
+    (``Code/Burgers_equation/Exact_Burger_RV_conv.py:81-86,223``, ``Code/Linear_advection/RV_node_convergence.py:49,239``)
+    -- ``Context.l2_error_p3``.  ``degree=1``: both fields in P1 (nodal values or a callable), mass-matrix norm."""
     ctx = domain if isinstance(domain, Context) else Context.for_domain(domain)
+    if degree == 3:
+        return ctx.l2_error_p3(_interpolate(ctx, uh), u_ref)
+    if degree != 1:
+        raise NotImplementedError("the error functional exists for a P1 or a P3 interpolant of the reference field")
     d = _interpolate(ctx, uh) - _interpolate(ctx, u_ref)
     Md = ctx.spmv(L.MAT_MASS, d)
     return float(np.sqrt(max(float(d @ Md), 0.0)))

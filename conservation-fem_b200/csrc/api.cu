@@ -309,6 +309,7 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
   dm.tile_order = upload(c, hm.tile_order);
   dm.n_interior = hm.n_interior_tiles;
   dm.last_cell = upload(c, hm.last_cell);
+  dm.cell_user = upload(c, hm.cell_user);
   c->d_n2u = upload(c, hm.n2u);
   c->d_u2n = world == 1 ? upload(c, hm.u2n) : nullptr;  // user -> local is only a permutation on one GPU
   c->d_send_idx = upload(c, hm.send_idx);
@@ -838,13 +839,16 @@ static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps,
       launch_si_epsilon(c, p->flux, si->Cm, si->floor, true, c->unit_stiffness, c->u_n, c->h, nullptr, nullptr, c->eps);
     }
     // (a-8) Newton on the Crank-Nicolson residual, dolfinx NewtonSolver 'residual' criterion
-    int np = launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, fluxn, F, normpart);
+    // the first evaluation assembles F and J together (one cell pass); CFEM_FUSED_FJ=0 keeps them apart
+    static const bool fused_fj = !(getenv("CFEM_FUSED_FJ") && std::string(getenv("CFEM_FUSED_FJ")) == "0");
+    int np = fused_fj ? launch_cn_residual_jacobian(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, fluxn, F, normpart, J)
+                      : launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, fluxn, F, normpart);
     double res = partials_norm(c, normpart, np);
     const double res0 = res;
     bool converged = res < p->newton_atol;
     int it = 0;
     while (!converged && it < p->newton_max_it) {
-      launch_cn_jacobian(c, p->flux, p->dt, c->uh, c->eps, J);
+      if (it > 0 || !fused_fj) launch_cn_jacobian(c, p->flux, p->dt, c->uh, c->eps, J);
       // The first Newton update of a step is close to the previous step's (the solution moves by nearly the
       // same amount): start the Krylov solve from it.  The solve still runs to lin_rtol, so only the
       // iteration count changes.  Later Newton iterations (tiny corrections) start from zero.
@@ -1102,6 +1106,36 @@ int cfem_step_euler(cfem_ctx* c, const cfem_step_params* p, int n_steps, cfem_st
   st.spmv_launches = c->launches.spmv - l0.spmv;
   st.assembly_launches = c->launches.assembly - l0.assembly;
   if (stats) *stats = st;
+  API_END
+}
+
+int cfem_l2_error_p3(cfem_ctx* c, const double* uh, const double* uex_cells, double* err_out) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!uex_cells || !err_out) CFEM_THROW(-1, "l2_error_p3: null argument");
+  if (uh) import_vec(c, uh, c->uh);
+  const int64_t nc = c->dm.nc;
+  // rows of the caller's (Nc_global, 10) table for this rank's cells, gathered on the host (or read in place on the device)
+  const double* table = uex_cells;
+  bool local_rows = false;
+  double* dtab = nullptr;
+  if (!is_device_ptr(uex_cells)) {
+    std::vector<double> rows(10 * (size_t)nc);
+    const int32_t* cu = c->hm.cell_user.data();
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < nc; ++k) {
+      const int64_t u = cu[k] >= 0 ? cu[k] : ~cu[k];
+      for (int a = 0; a < 10; ++a) rows[10 * k + a] = uex_cells[10 * u + a];
+    }
+    CUDA_OK(cudaMalloc((void**)&dtab, rows.size() * sizeof(double)));
+    CUDA_OK(cudaMemcpy(dtab, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+    table = dtab;
+    local_rows = true;
+  }
+  const double sq = launch_l2_error_p3(c, c->uh, table, local_rows);
+  if (dtab) cudaFree(dtab);
+  comm_check(c);
+  *err_out = sqrt(sq > 0.0 ? sq : 0.0);
   API_END
 }
 

@@ -340,6 +340,68 @@ struct CnJacobianOp {
   __device__ double node(int32_t, const double*) const { return 0.0; }
 };
 
+// F(uh) AND J = dF/duh in one cell pass: what the first Newton iteration of a step needs (same uh, u_n, eps, geometry;
+// the flux Jacobian the lifting of F uses is the one J is built from).  Saves a launch and a full gather pass per step.
+template <int FLUX, bool HAVE_FLUXN>
+struct CnResJacOp {
+  static constexpr int NV = 1;
+  static constexpr int MINB = 1;
+  static constexpr bool PREFETCH = true;
+  static constexpr bool MAT = true;
+  const double *uh, *u_n, *eps, *g, *fluxn;
+  const uint8_t* is_bc;
+  double hdt;  // dt/2
+  double* F;
+  __device__ void cell(const int32_t* v, const CellGeom& cg, int bcmask, double* evec, double* emat) const {
+    double u[3], un[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { u[k] = uh[v[k]]; un[k] = u_n[v[k]]; }
+    const double eb = (eps[v[0]] + eps[v[1]] + eps[v[2]]) * (1.0 / 3.0);
+    double f[3];
+    flux_vec<FLUX>(cg, u, f);
+    if (!HAVE_FLUXN) {
+      double fn[3];
+      flux_vec<FLUX>(cg, un, fn);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) f[a] += fn[a];
+    }
+    double J[9];
+    flux_jac<FLUX>(cg, u, J);
+    const double m = cg.area * (1.0 / 12.0);
+    const double d0 = u[0] - un[0], d1 = u[1] - un[1], d2 = u[2] - un[2], sd = d0 + d1 + d2;
+    const double dd[3] = {d0, d1, d2};
+    const double sx = (u[0] + un[0]) * cg.gx[0] + (u[1] + un[1]) * cg.gx[1] + (u[2] + un[2]) * cg.gx[2];
+    const double sy = (u[0] + un[0]) * cg.gy[0] + (u[1] + un[1]) * cg.gy[1] + (u[2] + un[2]) * cg.gy[2];
+    const double kf = hdt * eb * cg.area;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) evec[a] = m * (sd + dd[a]) + hdt * f[a] + kf * (sx * cg.gx[a] + sy * cg.gy[a]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        emat[a * 3 + b] = (a == b ? 2.0 * m : m) + hdt * J[a * 3 + b] + kf * (cg.gx[a] * cg.gx[b] + cg.gy[a] * cg.gy[b]);
+    if (bcmask) {
+      // lifting: F_a += J_ab (g_b - uh_b) over Dirichlet columns b (alpha = -1, x0 = uh); same expression order as
+      // CnResidualOp so that the two evaluations of F agree to the bit
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        if (bcmask & (1 << b)) {
+          const double dg = g[v[b]] - u[b];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) evec[a] += emat[a * 3 + b] * dg;
+        }
+      }
+    }
+  }
+  __device__ double node(int32_t i, const double* acc) const {
+    double f = acc[0];
+    if (HAVE_FLUXN) f += hdt * fluxn[i];
+    if (is_bc[i]) f = uh[i] - g[i];
+    F[i] = f;
+    return f * f;
+  }
+};
+
 // Linear advection Crank-Nicolson system (reference RV_node.py:220-242)
 struct AdvSystemOp {
   static constexpr int NV = 1;
@@ -618,6 +680,27 @@ int launch_cn_residual(cfem_ctx* c, int flux, double dt, const double* uh, const
     case CFEM_FLUX_KPP: return cn_residual_t<CFEM_FLUX_KPP>(c, dt, uh, u_n, eps, g, fluxn, F, partials);
     default: CFEM_THROW(-1, "cn_residual: flux must be BURGERS or KPP");
   }
+}
+
+template <int FLUX>
+static int cn_resjac_t(cfem_ctx* c, double dt, const double* uh, const double* u_n, const double* eps, const double* g,
+                       const double* fluxn, double* F, double* partials, Matrix& J) {
+  if (fluxn)
+    return run_tiles(c, CnResJacOp<FLUX, true>{uh, u_n, eps, g, fluxn, c->dm.is_bc, 0.5 * dt, F}, true, J.vals, J.dinv, partials);
+  return run_tiles(c, CnResJacOp<FLUX, false>{uh, u_n, eps, g, fluxn, c->dm.is_bc, 0.5 * dt, F}, true, J.vals, J.dinv, partials);
+}
+
+int launch_cn_residual_jacobian(cfem_ctx* c, int flux, double dt, const double* uh, const double* u_n,
+                                const double* eps, const double* g, const double* fluxn, double* F, double* partials,
+                                Matrix& J) {
+  int np = 0;
+  switch (flux) {
+    case CFEM_FLUX_BURGERS: np = cn_resjac_t<CFEM_FLUX_BURGERS>(c, dt, uh, u_n, eps, g, fluxn, F, partials, J); break;
+    case CFEM_FLUX_KPP: np = cn_resjac_t<CFEM_FLUX_KPP>(c, dt, uh, u_n, eps, g, fluxn, F, partials, J); break;
+    default: CFEM_THROW(-1, "cn_residual_jacobian: flux must be BURGERS or KPP");
+  }
+  J.valid = true;
+  return np;
 }
 
 void launch_cn_jacobian(cfem_ctx* c, int flux, double dt, const double* uh, const double* eps, Matrix& J) {

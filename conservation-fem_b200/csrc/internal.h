@@ -69,6 +69,8 @@ struct HostMesh {
   int n_interior_tiles = 0;
   std::vector<uint8_t> is_bnd;            // nn
   std::vector<int32_t> last_cell;         // n_owned: incident local cell with the highest caller index
+  std::vector<int32_t> cell_user;         // nc: caller index of each local cell; ~index (negative) for cells whose smallest
+                                          // vertex another rank owns (so cell-wise functionals count every cell once)
   std::vector<int32_t> bnd_user_sorted;   // boundary dofs, user ids ascending
   int max_row = 0, max_tile_cells = 0, max_tile_nnz = 0;
 };
@@ -106,6 +108,7 @@ struct DevMesh {
   int n_interior;              // number of tiles that need no ghost value
   const uint8_t* is_bc;    // current Dirichlet flags
   const int32_t* last_cell;  // per owned node, see HostMesh
+  const int32_t* cell_user;  // per local cell, see HostMesh
 };
 
 constexpr int kMaxPartials = 4096;   // >= any reduction grid

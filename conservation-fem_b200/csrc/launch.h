@@ -22,6 +22,10 @@ int launch_cn_residual(cfem_ctx* c, int flux, double dt, const double* uh, const
                        double* norm2_partials);
 void launch_cn_jacobian(cfem_ctx* c, int flux, double dt, const double* uh, const double* eps,
                         Matrix& J);
+// F(uh) and J(uh) in one cell pass (first Newton iteration of a step)
+int launch_cn_residual_jacobian(cfem_ctx* c, int flux, double dt, const double* uh, const double* u_n,
+                                const double* eps, const double* g, const double* fluxn, double* F,
+                                double* norm2_partials, Matrix& J);
 // A = M + S, b = (M - S) u_n with lifting, S = dt/2 (C_w + K_eps); eps nullable.
 void launch_adv_system(cfem_ctx* c, double dt, const double2* w, const double* eps,
                        const double* u_n, const double* g, Matrix& A, double* b);
@@ -111,6 +115,9 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
                     const double* u_n, double* Rh, const double* h, const double2* w, double* eps);
 void launch_si_epsilon(cfem_ctx* c, int flux, double Cm, double floor_, bool use_bc, const Matrix& K1, const double* u,
                        const double* h, const double2* w, double* psi, double* eps);
+// sum over this rank's cells (each cell counted by one rank) and over the ranks of  int_K (uh - I3 u_ex)^2 ; synchronous.
+// table: the exact solution at the ten P3 nodes per cell, rows by local cell (local_rows) or by caller cell index
+double launch_l2_error_p3(cfem_ctx* c, const double* uh, const double* table, bool local_rows);
 void launch_bc_values(cfem_ctx* c, int kind, double value, double t, const double* user_vals,
                       double* g);
 

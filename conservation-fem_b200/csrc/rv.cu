@@ -4,8 +4,13 @@
 // and the Dirichlet-value kernel.
 //
 // Restates the per-node Python loops of the reference, Code/Utils/RV.py:27-142.
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+
 #include "device_utils.cuh"
 #include "launch.h"
+#include "p2p.cuh"
 
 namespace cfem {
 
@@ -123,6 +128,83 @@ k_epsilon_stream(const int ntiles, const int64_t nn, const int32_t* __restrict__
   }
 }
 
+// Same formulas, one gather pass (default).  The tile's patch values are staged ONCE per tile in the T16 layout of the
+// SpMV-type kernels -- own rows coalesced, the ~100 external columns gathered -- for all three fields at a time
+// (u_n, |Rh|, ||f'(uh)|| computed on the fly: no beta table is written or read), the 16-bit tile-local columns are
+// staged coalesced, and thread r reduces row r's patch out of shared memory.  Replaces three serial gather passes
+// over 32-bit columns with four barriers each (77 us -> see profiles/ at 1 M nodes).
+template <bool LINEAR, int FLUX>
+__global__ void __launch_bounds__(kTileNodes)
+k_epsilon_t16(const int ntiles, const int64_t nn, const int ext_cap, const int32_t* __restrict__ tile_node,
+              const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ lc16, const int32_t* __restrict__ extptr,
+              const int32_t* __restrict__ ext, const double* __restrict__ uh, const double* __restrict__ u_n,
+              const double* __restrict__ Rh, const double2* __restrict__ w, const double* __restrict__ h,
+              const double* __restrict__ part, int npart, double Cvel, double Crv, double* __restrict__ eps) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ double eps_smem[];
+  const int span = kTileNodes + ext_cap;
+  double* const s_un = eps_smem;             // [span]
+  double* const s_r = eps_smem + span;       // [span]
+  double* const s_b = eps_smem + 2 * span;   // [span] (nonlinear variants)
+  uint16_t* const s_lc = (uint16_t*)(eps_smem + 3 * span);   // [kTileNnzCap]
+  __shared__ int32_t rp[kTileNodes + 1];
+  __shared__ double red[9];
+  const double A = absolute_term(part, npart, nn, red);
+  const int tid = threadIdx.x;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n0 = tile_node[tile], nrows = tile_node[tile + 1] - n0;
+    const int e0 = extptr[tile], ne = extptr[tile + 1] - e0;
+    const int start = rowptr[n0], cnt = rowptr[n0 + nrows] - start;
+    for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i] - start;
+    for (int p = tid; p < cnt; p += kTileNodes) s_lc[p] = lc16[start + p];
+    for (int e = tid; e < nrows + ne; e += kTileNodes) {
+      const int j = e < nrows ? n0 + e : ext[e0 + e - nrows];
+      const int slot = e < nrows ? e : kTileNodes + (e - nrows);
+      s_un[slot] = u_n[j];
+      s_r[slot] = fabs(Rh[j]);
+      if (!LINEAR) s_b[slot] = beta_of<FLUX>(uh[j]);
+    }
+    __syncthreads();
+    if (tid < nrows) {
+      double umax = -INFINITY, umin = INFINITY, rmax = 0.0, bmax = 0.0;
+      for (int k = rp[tid]; k < rp[tid + 1]; ++k) {
+        const int j = s_lc[k];
+        const double un = s_un[j];
+        umax = fmax(umax, un);
+        umin = fmin(umin, un);
+        rmax = fmax(rmax, s_r[j]);
+        if (!LINEAR) bmax = fmax(bmax, s_b[j]);
+      }
+      const int row = n0 + tid;
+      if (LINEAR) {
+        const double2 wi = w[row];  // centre node, RV.py:113-115
+        bmax = sqrt(__dadd_rn(__dmul_rn(wi.x, wi.x), __dmul_rn(wi.y, wi.y)));
+      }
+      const double hi = h[row];
+      const double n_i = fabs((umax - umin) - A);
+      const double Ri = rmax / n_i;
+      const double first = __dmul_rn(__dmul_rn(Cvel, hi), bmax);
+      const double second = __dmul_rn(__dmul_rn(Crv, __dmul_rn(hi, hi)), fabs(Ri));
+      eps[row] = pymin(first, second);
+    }
+    __syncthreads();
+  }
+}
+
+template <bool LINEAR, int FLUX>
+static void launch_epsilon_t16(cfem_ctx* c, const double* uh, const double* u_n, const double* Rh, const double2* w,
+                               const double* h, int np, double Cvel, double Crv, double* eps) {
+  const DevMesh& m = c->dm;
+  const size_t smem = sizeof(double) * 3 * (size_t)(kTileNodes + m.ext_cap) + sizeof(uint16_t) * (size_t)kTileNnzCap;
+  if (smem > kDynSmemCeiling) CFEM_THROW(-2, "epsilon kernel: a tile has too many external columns for shared memory");
+  CUDA_OK(cudaFuncSetAttribute(k_epsilon_t16<LINEAR, FLUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemCeiling));
+  int64_t g = (int64_t)c->sm_count * 8;
+  if (g > m.ntiles) g = m.ntiles;
+  launch_pdl(k_epsilon_t16<LINEAR, FLUX>, (int)g, kTileNodes, smem, c->stream, m.ntiles, m.nn_global, m.ext_cap, m.tile_node,
+             m.rowptr, m.lc16, m.tile_extptr, m.tile_ext, uh, u_n, Rh, w, h, c->partials, np, Cvel, Crv, eps);
+}
+
 // pointwise variants: RV.get_epsilon (RV.py:27-40), get_epsilon_1storder (RV.py:42-54),
 // get_epsilon_linear_simple (RV.py:129-142; also normalises Rh in place)
 template <int FLUX>
@@ -225,6 +307,20 @@ void launch_epsilon(cfem_ctx* c, int variant, int flux, double Cvel, double Crv,
   if (!h) CFEM_THROW(-1, "rv_epsilon: nodal mesh size h is required");
   if (variant == CFEM_EPS_NONLINEAR || variant == CFEM_EPS_LINEAR) {
     if (!uh || !u_n || !Rh) CFEM_THROW(-1, "rv_epsilon: uh, u_n and Rh are required");
+    static const bool one_pass = !(getenv("CFEM_EPS") && std::string(getenv("CFEM_EPS")) == "3pass");
+    if (one_pass) {
+      if (variant == CFEM_EPS_LINEAR && !w) CFEM_THROW(-1, "rv_epsilon(linear): velocity field w is required");
+      if (variant == CFEM_EPS_NONLINEAR && flux != CFEM_FLUX_BURGERS && flux != CFEM_FLUX_KPP)
+        CFEM_THROW(-1, "rv_epsilon(nonlinear): flux must be BURGERS or KPP");
+      launch_pdl(k_stats<-1>, gv, kBlock, 0, c->stream, n, nl, uh, nullptr, c->partials); LAUNCHED(c);
+      np = stats_allreduce(c, gv);
+      if (variant == CFEM_EPS_LINEAR) launch_epsilon_t16<true, CFEM_FLUX_BURGERS>(c, uh, u_n, Rh, w, h, np, Cvel, Crv, eps);
+      else if (flux == CFEM_FLUX_BURGERS) launch_epsilon_t16<false, CFEM_FLUX_BURGERS>(c, uh, u_n, Rh, w, h, np, Cvel, Crv, eps);
+      else launch_epsilon_t16<false, CFEM_FLUX_KPP>(c, uh, u_n, Rh, w, h, np, Cvel, Crv, eps);
+      LAUNCHED(c);
+      halo_exchange(c, eps);
+      return;
+    }
     double* beta = c->wk[9];
     if (variant == CFEM_EPS_LINEAR) {
       if (!w) CFEM_THROW(-1, "rv_epsilon(linear): velocity field w is required");
@@ -381,6 +477,113 @@ void launch_bc_values(cfem_ctx* c, int kind, double value, double t, const doubl
   ProfScope ps(c, PROF_MISC);
   k_bc_values<<<vec_grid(c, c->nbc), kBlock, 0, c->stream>>>(c->nbc, c->d_bc_nodes, c->d_bc_pos, kind, value, t, user_vals, c->dm.xy, g);
   LAUNCHED(c);
+}
+
+// ---------------------------------------------------------------- (f-2) L2 error against a P3 interpolant
+// P3 mass matrix of the reference triangle, int phi_a phi_b / |K| (x 6720; symmetric).  Node order: vertices 0 1 2, edge
+// opposite vertex 0 (1/3 and 2/3 of the way from vertex 1 to 2), edge opposite 1 (from 0 to 2), edge opposite 2
+// (from 0 to 1), centroid.  Filled once from the closed form  int l0^a l1^b l2^c = 2|K| a! b! c! / (a+b+c+2)! .
+__constant__ double kM3[10][10];
+
+static void fill_m3(double M[10][10]) {
+  // basis in barycentric monomials: coefficient arrays over exponents (a,b,c) with a+b+c <= 3
+  struct Poly { double c[4][4][4]; };
+  auto zero = []() { Poly p; for (auto& x : p.c) for (auto& y : x) for (auto& z : y) z = 0.0; return p; };
+  auto mul_lin = [&](const Poly& p, int i, double a, double b) {   // p * (a l_i + b)
+    Poly r = zero();
+    for (int x = 0; x < 4; ++x) for (int y = 0; y < 4; ++y) for (int z = 0; z < 4; ++z) {
+      const double v = p.c[x][y][z];
+      if (v == 0.0) continue;
+      r.c[x][y][z] += b * v;
+      const int nx = x + (i == 0), ny = y + (i == 1), nz = z + (i == 2);
+      if (nx < 4 && ny < 4 && nz < 4) r.c[nx][ny][nz] += a * v;
+    }
+    return r;
+  };
+  Poly one = zero();
+  one.c[0][0][0] = 1.0;
+  Poly phi[10];
+  for (int i = 0; i < 3; ++i) {   // 1/2 l (3l-1)(3l-2)
+    phi[i] = mul_lin(mul_lin(mul_lin(one, i, 0.5, 0.0), i, 3.0, -1.0), i, 3.0, -2.0);
+  }
+  const int edge[6][2] = {{1, 2}, {2, 1}, {0, 2}, {2, 0}, {0, 1}, {1, 0}};   // (near vertex, far vertex)
+  for (int k = 0; k < 6; ++k) phi[3 + k] = mul_lin(mul_lin(mul_lin(one, edge[k][0], 4.5, 0.0), edge[k][1], 1.0, 0.0), edge[k][0], 3.0, -1.0);
+  phi[9] = mul_lin(mul_lin(mul_lin(one, 0, 27.0, 0.0), 1, 1.0, 0.0), 2, 1.0, 0.0);
+  auto fact = [](int n) { double f = 1.0; for (int k = 2; k <= n; ++k) f *= k; return f; };
+  for (int a = 0; a < 10; ++a)
+    for (int b = 0; b < 10; ++b) {
+      double s = 0.0;
+      for (int x = 0; x < 4; ++x) for (int y = 0; y < 4; ++y) for (int z = 0; z < 4; ++z) {
+        const double va = phi[a].c[x][y][z];
+        if (va == 0.0) continue;
+        for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q) for (int r = 0; r < 4; ++r) {
+          const double vb = phi[b].c[p][q][r];
+          if (vb == 0.0) continue;
+          const int ex = x + p, ey = y + q, ez = z + r;
+          s += va * vb * 2.0 * fact(ex) * fact(ey) * fact(ez) / fact(ex + ey + ez + 2);
+        }
+      }
+      M[a][b] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_l2_error_p3(const int64_t nc, const int32_t* __restrict__ cells, const double2* __restrict__ xy,
+              const int32_t* __restrict__ cell_user, const double* __restrict__ uh, const double* __restrict__ table,
+              const int local_rows, double* __restrict__ partials, const Fin fin, double* __restrict__ out) {
+  __shared__ double red[9];
+  __shared__ double sums[1];
+  double acc = 0.0;
+  for (int64_t c = blockIdx.x * (int64_t)kBlock + threadIdx.x; c < nc; c += (int64_t)gridDim.x * kBlock) {
+    const int32_t cu = cell_user[c];
+    if (cu < 0) continue;   // counted by the rank that owns the cell's smallest vertex
+    const int v0 = cells[3 * c], v1 = cells[3 * c + 1], v2 = cells[3 * c + 2];
+    const double2 p0 = xy[v0], p1 = xy[v1], p2 = xy[v2];
+    const double area = 0.5 * fabs((p1.x - p0.x) * (p2.y - p0.y) - (p1.y - p0.y) * (p2.x - p0.x));
+    const double u0 = uh[v0], u1 = uh[v1], u2 = uh[v2];
+    const double t3 = 1.0 / 3.0;
+    // the P1 function at the ten P3 nodes (exact embedding), minus the exact solution there
+    double e[10] = {u0, u1, u2,
+                    t3 * (2.0 * u1 + u2), t3 * (u1 + 2.0 * u2),
+                    t3 * (2.0 * u0 + u2), t3 * (u0 + 2.0 * u2),
+                    t3 * (2.0 * u0 + u1), t3 * (u0 + 2.0 * u1),
+                    t3 * (u0 + u1 + u2)};
+    const double* row = table + 10 * (local_rows ? c : (int64_t)cu);
+#pragma unroll
+    for (int a = 0; a < 10; ++a) e[a] -= row[a];
+    double q = 0.0;
+#pragma unroll
+    for (int a = 0; a < 10; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < 10; ++b) s += kM3[a][b] * e[b];
+      q += e[a] * s;
+    }
+    acc += q * area;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+  Slots<1> sl;
+  sl.p[0] = partials;
+  if (fin_reduce<1>(fin, sl, gridDim.x, red, sums) && threadIdx.x == 0) out[0] = sums[0];
+}
+
+double launch_l2_error_p3(cfem_ctx* c, const double* uh, const double* table, bool local_rows) {
+  static bool filled = false;
+  static double M[10][10];
+  if (!filled) { fill_m3(M); filled = true; }
+  CUDA_OK(cudaMemcpyToSymbol(kM3, M, sizeof(M)));   // per call: constant memory is per device, the table is tiny
+  if (!fin_available(c)) CFEM_THROW(-1, "l2_error_p3 needs the in-kernel reductions (one GPU or the peer-memory path)");
+  const int64_t nc = c->dm.nc;
+  int g = (int)std::min<int64_t>((nc + kBlock - 1) / kBlock, (int64_t)c->sm_count * 8);
+  if (g < 1) g = 1;
+  k_l2_error_p3<<<g, kBlock, 0, c->stream>>>(nc, c->dm.cells, c->dm.xy, c->dm.cell_user, uh, table, local_rows ? 1 : 0,
+                                             c->partials + 7 * kMaxPartials, make_fin(c), c->scalars + 25);
+  CUDA_OK(cudaGetLastError());
+  c->launches.total++;
+  CUDA_OK(cudaMemcpyAsync(c->h_pinned + 16, c->scalars + 25, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return c->h_pinned[16];
 }
 
 }  // namespace cfem

@@ -255,6 +255,10 @@ static void build_part(const GlobalOrder& g, const double* x, int xdim, const vo
   for (int64_t c = 0; c < nc; ++c)
     for (int k = 0; k < 3; ++k) hm.cells[3 * c + k] = to_local(lc[c].v[k]);
 
+  hm.cell_user.resize(nc);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < nc; ++c) hm.cell_user[c] = (lc[c].vmin >= lo && lc[c].vmin < hi) ? lc[c].user : ~lc[c].user;
+
   // vertex -> (cell, k) of the owned nodes, cells ascending
   hm.v2c_ptr.assign(no + 1, 0);
   for (int64_t e = 0; e < 3 * nc; ++e)

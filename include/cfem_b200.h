@@ -299,6 +299,15 @@ enum { CFEM_KERNEL_SPMV = 0, CFEM_KERNEL_ASM_RESIDUAL = 1, CFEM_KERNEL_ASM_JACOB
  *   7 communication (halo pack + NCCL send/recv, all-reduce)            (arrays of 8) */
 int cfem_profile_begin(cfem_ctx* ctx, int max_launches);
 int cfem_profile_end(cfem_ctx* ctx, double* ms_per_category, int64_t* launches_per_category);
+/* L2 error against a P3 interpolant of the exact solution (f-2):  sqrt( int (uh - I3 u_ex)^2 dx ), the functional of
+ * Code/Burgers_equation/Exact_Burger_RV_conv.py:81-86,223 and Code/Linear_advection/RV_node_convergence.py:49,69-70,239
+ * (u_exact = Function(P3).interpolate(exact); assemble_scalar((uh - u_exact)**2 * dx)).  uh: P1 nodal values (NULL: the
+ * resident uh); uex_cells: (n_cells, 10) values of the exact solution at the P3 Lagrange nodes of every CALLER cell, in
+ * the order 3 vertices (the cell's own vertex order), 2 nodes on the edge opposite vertex 0, 1, 2 (each one third and
+ * two thirds of the way, see cfem_b200/context.py: p3_cell_points), centroid.  Distributed: every rank passes the whole
+ * table and gets the global value.  Evaluated in closed form with the 10 x 10 P3 mass matrix (the integrand has
+ * degree 6; dolfinx uses a 12-point degree-6 rule -- same value). */
+int cfem_l2_error_p3(cfem_ctx* ctx, const double* uh, const double* uex_cells, double* err_out);
 int cfem_time_kernel(cfem_ctx* ctx, int kernel, int flux, int reps, double* ms_per_launch,
                      double* algorithmic_bytes);
 
