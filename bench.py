@@ -222,7 +222,7 @@ def run_euler(args, device):
     X3[0], X3[1] = x[:, 0], x[:, 1]
     U0 = GS.sod_initial_condition(X3, 1.0)
     dt = 0.25 / n
-    p = step_params("burgers", dt, 0.5, 4.0, scheme="bdf2", newton_rtol=1e-4, lin_rtol=1e-13)
+    p = step_params("burgers", dt, 0.5, 4.0, scheme="bdf2", newton_rtol=1e-4, lin_rtol=1e-13)   # Euler keeps the plain-norm solver
     ctx.euler_state_set(Uh=U0, Un=U0, Uold=U0, Uoo=U0, bc_state=U0, h=h, t=0.0)
     ctx.step_euler(p, W)
     with ClockSampler(device) as clk:
@@ -236,6 +236,38 @@ def run_euler(args, device):
         ctx.step_euler(p, 1)
         ctx.euler_state_get(("Uh",))
     e2e_s = (time.perf_counter() - t0) / min(K, 5)
+    # roofline of the dominant kernel, k_apply4 (matrix-free 4-component Jacobian / residual apply, thread per row):
+    # algorithmic bytes of one Jacobian-vector product = three scalar CSR value arrays + the shared pattern, three
+    # gathered 4-component inputs (x, Ax(U)x, Ay(U)x), one 4-component output.  Timed with one CUDA-event pair per launch
+    # on the context stream (the launches alternate with vector kernels: no back-to-back run exists).
+    nnz = ctx.nnz
+    peak, peak_src = measured_peak()
+    apply_bytes = 28.0 * nnz + 4.0 * (nn + 1) + 4 * 32.0 * nn
+    ms = prof["spmv"]["ms"] / max(prof["spmv"]["launches"], 1)
+    tot = sum(v["ms"] for v in prof.values())
+    roofline = {"bound": "hbm", "kernel": "k_apply4 (4-component CSR apply of the matrix-free Euler Jacobian; thread per row, "
+                                          "not yet tile-staged like the scalar kernels)",
+                "achieved": apply_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": apply_bytes / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": apply_bytes, "avg_launch_ms": ms, "launches": prof["spmv"]["launches"],
+                "timing": "one CUDA-event pair per launch on the context stream",
+                "share_of_step": prof["spmv"]["ms"] / tot if tot else None}
+    cpu = None
+    if not args.no_cpu_baseline:
+        # bounded sample: the same scheme (oracle/euler.py: numpy + SuperLU on the 4N x 4N Jacobian) on a 128 x 64 x 2
+        # mesh -- a direct LU at 16 M unknowns is out of reach, so the sample is a smaller mesh and says so
+        from oracle import euler as E
+
+        ns = 64
+        xs, cs = meshes.rectangle(2 * ns, ns, (0.0, 0.0), (2.0, 1.0))
+        E.run_euler(xs, cs, 0.25 / ns, 1)
+        t0 = time.perf_counter()
+        E.run_euler(xs, cs, 0.25 / ns, 3)
+        el = time.perf_counter() - t0
+        cpu = {"value": 4 * xs.shape[0] * 3 / el, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"Euler RV {2 * ns}x{ns}x2 = {cs.shape[0]} cells ({4 * xs.shape[0]} dofs), 3 steps from the Sod data incl. "
+                         f"set-up, numpy/scipy oracle with SuperLU (the scheme is this repository's own, DESIGN.md section 7); "
+                         f"{el:.1f} s.  NOT the benchmark's mesh: a sparse LU of its 16 M x 16 M Jacobian is not feasible"}
     line = {"metric": METRIC, "value": 4 * nn * K / (st["device_ms"] * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K,
             "warmup": W, "ms_per_step": st["device_ms"] / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -245,7 +277,7 @@ def run_euler(args, device):
                        "krylov_its_per_step": st["krylov_iterations"] / K,
                        "mass_its_per_step": st["mass_iterations"] / K,
                        "scheme": "defined by this repository (no reference solver exists): DESIGN.md section 7"},
-            "roofline": None, "cpu_baseline": None,
+            "roofline": roofline, "cpu_baseline": cpu,
             "breakdown_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
             "e2e": {"value": 4 * nn / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * 32 * nn, "d2h_bytes_per_step": 32 * nn},
             "gpu_launches": int(st["kernel_launches"]), "clocks": clk.summary()}

@@ -205,10 +205,15 @@ def read_mesh(path):
 class XdmfWriter:
     """``io.XDMFFile(comm, path, "w")`` + ``write_mesh`` + ``write_function(f, t)`` of the reference loops."""
 
-    def __init__(self, path, x, cells, heavy="binary"):
+    def __init__(self, path, x, cells, heavy="binary", flush_every=16):
         """``heavy="binary"``: raw little-endian sidecar ``<name>.bin``; ``heavy="hdf5"``: ``<name>.h5`` laid out
-        like dolfinx's (``/Mesh/mesh/{topology,geometry}``, ``/Function/<name>/<t with . -> _>``)."""
+        like dolfinx's (``/Mesh/mesh/{topology,geometry}``, ``/Function/<name>/<t with . -> _>``).
+        ``flush_every``: the XML (and, for hdf5, the file's metadata tree, which is re-appended whole on every flush)
+        is brought up to date every that many frames and on ``close()`` -- per-frame flushes made both grow
+        quadratically with the number of frames."""
         self.path = path
+        self._flush_every = max(1, int(flush_every))
+        self._unflushed = 0
         folder = os.path.dirname(os.path.abspath(path))
         stem = os.path.splitext(os.path.basename(path))[0]
         x = np.ascontiguousarray(x, dtype="<f8")
@@ -240,14 +245,30 @@ class XdmfWriter:
         a = np.ascontiguousarray(a, dtype="<f8").reshape(self.nn, -1)
         name = name or getattr(f, "name", "f")
         if self._h5:
-            where = f"/Function/{name}/{repr(float(t)).replace('.', '_')}"
+            # dolfinx names the dataset boost::lexical_cast<std::string>(t) with '.' -> '_': 17 significant digits,
+            # no trailing zeros ("1", "0_01", "0_30000000000000004"), i.e. C's %.17g -- not Python's repr ("1.0")
+            base = f"/Function/{name}/{format(float(t), '.17g').replace('.', '_')}"
+            where, k = base, 0
+            taken = {w for (_, _, w, _) in self._frames}
+            while where in taken:      # the same (name, t) written twice: keep both frames
+                k += 1
+                where = f"{base}_{k}"
             self._h5.write(where, a)
-            self._h5.flush()
         else:
             where = self._append(a)
-            self._bin.flush()
         self._frames.append((name, float(t), where, a.shape[1]))
+        self._unflushed += 1
+        if self._unflushed >= self._flush_every:
+            self.flush()
+
+    def flush(self):
+        """Make the files on disk complete and consistent up to the last frame written."""
+        if self._h5:
+            self._h5.flush()
+        else:
+            self._bin.flush()
         self._flush_xml()
+        self._unflushed = 0
 
     def _item(self, dims, kind, prec, where):
         if self._h5:
@@ -285,6 +306,8 @@ class XdmfWriter:
         os.replace(tmp, self.path)
 
     def close(self):
+        if self._bin or self._h5:
+            self.flush()
         if self._bin:
             self._bin.close()
             self._bin = None
@@ -400,7 +423,7 @@ class H5Writer:
         depth = 0
         while True:
             groups = self._balanced(level, self._TREE_MAX)
-            size = 24 + 8 * (2 * self._TREE_MAX + 1) + 8 * 2 * self._TREE_MAX
+            size = 24 + 8 * (self._TREE_MAX + 1) + 8 * self._TREE_MAX   # header + 2K+1 keys + 2K children (_TREE_MAX = 2K)
             addrs = [self._alloc(b"\0" * size) for _ in groups]
             nxt, left_key = [], 0
             for i, g in enumerate(groups):

@@ -255,6 +255,8 @@ def solve_advection(domain, initial_condition=advection_initial_condition, veloc
     u0 = _interpolate(ctx, initial_condition)
     w = _interpolate(ctx, velocity)
     if dt is None:
+        if hmax is None:
+            raise ValueError("pass dt, or hmax (the mesh size the reference feeds gmsh, RV_node.py:82-86) to derive it")
         dt = advection_dt(w, hmax, CFL)
     if num_steps is None:
         num_steps = int(np.ceil(T / dt))
@@ -314,6 +316,12 @@ def solve_euler(domain, initial_condition=sod_initial_condition, dt=None, num_st
     if U0.shape != (ctx.n, 4):
         raise ValueError("the Euler state must have shape (N, 4): rho, m1, m2, E")
     h = ctx.nodal_h() if h is None else _interpolate(ctx, h)
+    if dt is None:
+        # no reference value exists (the reference's Euler script never ran); CFL 0.25 on the sound speed of the data
+        rho, E = U0[:, 0], U0[:, 3]
+        q2 = (U0[:, 1] ** 2 + U0[:, 2] ** 2) / rho ** 2
+        c = np.sqrt(GAMMA * (GAMMA - 1.0) * (E / rho - 0.5 * q2))
+        dt = 0.25 * float(np.min(h)) / float(np.max(np.sqrt(q2) + c))
     ctx.euler_state_set(Uh=U0, Un=U0, Uold=U0, Uoo=U0, bc_state=U0, h=h, t=0.0)
     p = step_params(L.FLUX_BURGERS, dt, Cvel, Crv, scheme="bdf2", newton_rtol=newton_rtol, lin_rtol=lin_rtol)
     stats = ctx.step_euler(p, num_steps)
@@ -333,6 +341,8 @@ def solve_advection_rk4(domain, initial_condition=advection_initial_condition, v
     u = _interpolate(ctx, initial_condition).copy()
     w = _interpolate(ctx, velocity)
     if dt is None:
+        if hmax is None:
+            raise ValueError("pass dt, or hmax (the mesh size the reference feeds gmsh, RV_node.py:82-86) to derive it")
         dt = advection_dt(w, hmax, CFL)
     if num_steps is None:
         num_steps = int(np.ceil(T / dt))

@@ -25,6 +25,7 @@ def test_xdmf_writer_roundtrip(tmp_path):
             frames.append(uh.x.array.copy())
             w.write_function(uh, t)                            # xdmf.write_function(uh, t)
             if k == 1:                                         # readable while the run is still going
+                w.flush()                                      # (files are brought up to date every flush_every frames / on flush)
                 d = io.read_xdmf(path)
                 assert d["series"]["uh"][1].shape == (2, x.shape[0])
         w.write_function(vec, 0.4, name="w")
