@@ -92,7 +92,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------- CPU arm
-def cpu_burgers_run(n=1024, steps=2, warm=1):
+def cpu_burgers_run(n=1024, steps=2, warm=1, h=None):
     """The oracle's Burgers RV loop (numpy + SuperLU; Exact_Burger_RV.py:169-237 restated) on the workload's OWN mesh:
     `warm` untimed steps, then `steps` timed ones.  Set-up (mesh relations, mass LU, h_CG) is outside the timed region,
     as the context creation is on the GPU side."""
@@ -102,7 +102,8 @@ def cpu_burgers_run(n=1024, steps=2, warm=1):
     t_setup = time.perf_counter()
     x, c = meshes.rectangle(n, n)
     m = S.Mesh(x, c)
-    h = p1.nodal_h(x, c)
+    if h is None:
+        h = p1.nodal_h(x, c)   # (the GPU arm hands over its own h_CG: one sparse LU less in the untimed set-up)
     m.mass_lu(True)
     u0 = S.burgers_initial_condition(x)
     st = S.ScalarState(u0.copy(), u0.copy(), u0.copy(), u0.copy(), np.zeros(m.n))
@@ -552,7 +553,8 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_burgers_run(n=n if args.workload == "burgers" else 1024, steps=args.cpu_steps, warm=0)
+        same = args.workload == "burgers"
+        cpu, _ = cpu_burgers_run(n=n if same else 1024, steps=args.cpu_steps, warm=0, h=ctx.nodal_h() if same else None)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
