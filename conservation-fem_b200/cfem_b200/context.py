@@ -351,14 +351,14 @@ class Context:
         L.check(self._lib.cfem_time_kernel(self._h, int(kernel), _flux(flux), int(reps), C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
-    PROFILE_CATEGORIES = ("spmv", "asm_vector", "asm_matrix", "krylov_vector", "rv", "misc", "chebyshev", "comm")
+    PROFILE_CATEGORIES = ("spmv", "asm_vector", "asm_matrix", "krylov_vector", "rv", "misc", "chebyshev", "comm", "solver")
 
     def profile_begin(self, max_launches=200000):
         L.check(self._lib.cfem_profile_begin(self._h, int(max_launches)))
 
     def profile_end(self):
-        ms = (C.c_double * 8)()
-        cnt = (C.c_int64 * 8)()
+        ms = (C.c_double * len(self.PROFILE_CATEGORIES))()
+        cnt = (C.c_int64 * len(self.PROFILE_CATEGORIES))()
         L.check(self._lib.cfem_profile_end(self._h, ms, cnt))
         return {k: {"ms": ms[i], "launches": cnt[i]} for i, k in enumerate(self.PROFILE_CATEGORIES)}
 

@@ -288,17 +288,16 @@ static int create_impl(cfem_ctx** out, int device, int rank, int world, const vo
     dm.ext_cap = (hm.max_tile_ext + 31) / 32 * 32;
     std::vector<uint16_t>().swap(hm.lc16);
     std::vector<int32_t>().swap(hm.tile_ext);
-    // persisting-L2 set-aside (device wide): as much as the device allows unless CFEM_L2_SETASIDE_MB says otherwise
+    // persisting-L2 set-aside: what the device allows unless CFEM_L2_SETASIDE_MB says otherwise.  It is a DEVICE-wide
+    // limit that shrinks the L2 every other access sees, so it is only switched on while a solve whose matrix fits is
+    // running (linalg.cu: l2_prefer / l2_release) -- a context whose matrices are too large, or the Euler path, must
+    // not pay for it (Euler 8 M cells: 81 -> 60 ms per step).
     const char* l2off = getenv("CFEM_L2PERSIST");
     if (!(l2off && std::string(l2off) == "0") && prop.persistingL2CacheMaxSize > 0) {
       size_t want = (size_t)prop.persistingL2CacheMaxSize;
       if (const char* mb = getenv("CFEM_L2_SETASIDE_MB")) want = std::min(want, (size_t)atol(mb) << 20);
-      if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-        c->l2_setaside = want;
-        c->l2_max_window = (size_t)prop.accessPolicyMaxWindowSize;
-      } else {
-        cudaGetLastError();
-      }
+      c->l2_setaside = want;
+      c->l2_max_window = (size_t)prop.accessPolicyMaxWindowSize;
     }
   }
   dm.v2c_ptr = upload(c, hm.v2c_ptr);
@@ -426,6 +425,7 @@ void cfem_destroy(cfem_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  l2_release(c);
   comm_destroy(c);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   for (void* p : c->allocs) cudaFree(p);
@@ -1094,6 +1094,7 @@ int cfem_step_euler(cfem_ctx* c, const cfem_step_params* p, int n_steps, cfem_st
   EventPair ev;
   TimeGuard tguard(c);
   cudaEvent_t ev0 = ev.a, ev1 = ev.b;
+  l2_release(c);   // the Euler kernels stream far more than the L2 holds: give them all of it
   CUDA_OK(cudaEventRecord(ev0, c->stream));
   euler_steps(c, p, n_steps, &st);
   CUDA_OK(cudaEventRecord(ev1, c->stream));

@@ -124,7 +124,7 @@ struct Launches {  // counters of our own kernel launches
 };
 
 // Optional per-launch CUDA-event bracketing (bench.py roofline leg).
-enum { PROF_SPMV = 0, PROF_ASM_VEC = 1, PROF_ASM_MAT = 2, PROF_KRYLOV_VEC = 3, PROF_RV = 4, PROF_MISC = 5, PROF_CHEB = 6, PROF_COMM = 7, PROF_NCAT = 8 };
+enum { PROF_SPMV = 0, PROF_ASM_VEC = 1, PROF_ASM_MAT = 2, PROF_KRYLOV_VEC = 3, PROF_RV = 4, PROF_MISC = 5, PROF_CHEB = 6, PROF_COMM = 7, PROF_SOLVER = 8, PROF_NCAT = 9 };
 struct Profiler {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs
@@ -207,5 +207,5 @@ struct cfem_ctx {
   std::vector<std::pair<const void*, int>> asm_occ;   // occupancy of the assembly kernel instantiations on this context
   void* persist_plan = nullptr;          // launch plan of the persistent BiCGStab kernel (persist.cu)
   int t16_grid = 0;                      // grid of the T16 tile kernels (occupancy x SMs, <= tiles), 0 = not sized yet
-  int l2_window = 0;                     // matrix id whose window is currently attached to the stream, -1 none
+  int l2_window = -1;                     // matrix id whose window is currently attached to the stream, -1 none
 };

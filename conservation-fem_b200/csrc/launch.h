@@ -71,6 +71,8 @@ double norm2(cfem_ctx* c, const double* v, int64_t n);  // synchronous
 // Attach the access-policy window of matrix A (values + pattern -> persisting L2 lines) to the context stream;
 // no-op for matrices outside the hot block or when CFEM_L2PERSIST=0.
 void l2_prefer(cfem_ctx* c, const Matrix& A);
+// detach the window and give the persisting set-aside back to the device
+void l2_release(cfem_ctx* c);
 
 // ---- multi-GPU (comm.cu); every call is a no-op when world == 1 --------------------
 void comm_unique_id(void* out128);

@@ -52,6 +52,16 @@ static inline bool use_t16() {
 // [rowptr | colidx | values] (SYSTEM) of the hot block; when it is larger than the set-aside, hitRatio keeps a
 // fixed random subset of its lines persisting instead of letting them thrash.  Vector traffic misses as
 // "streaming" lines, which are the first to be evicted.
+// device-wide persisting set-aside currently in force, per device (the limit belongs to the device, not to a context)
+static size_t g_l2_limit[64] = {0};
+static void l2_set_limit(cfem_ctx* c, size_t bytes) {
+  const int d = c->device < 64 ? c->device : 63;
+  if (g_l2_limit[d] == bytes) return;
+  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) { cudaGetLastError(); return; }
+  if (bytes == 0) cudaCtxResetPersistingL2Cache();   // lines that were persisting go back to normal replacement
+  g_l2_limit[d] = bytes;
+}
+
 void l2_prefer(cfem_ctx* c, const Matrix& A) {
   if (!c->l2_setaside) return;
   int which = -1;
@@ -67,6 +77,7 @@ void l2_prefer(cfem_ctx* c, const Matrix& A) {
     // traffic and costs the vectors the L2 capacity they were using (4 M-cell KPP: 15.7 -> 22 ms per step)
     if (bytes > c->l2_setaside || (c->l2_max_window && bytes > c->l2_max_window)) which = -1;
   }
+  l2_set_limit(c, which >= 0 ? c->l2_setaside : 0);
   if (which == c->l2_window) return;
   cudaStreamAttrValue attr{};
   if (which >= 0) {
@@ -80,6 +91,17 @@ void l2_prefer(cfem_ctx* c, const Matrix& A) {
   }
   CUDA_OK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
   c->l2_window = which;
+}
+
+void l2_release(cfem_ctx* c) {
+  if (!c->l2_setaside) return;
+  if (c->l2_window >= 0) {
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    c->l2_window = -1;
+  }
+  l2_set_limit(c, 0);
 }
 
 // ---------------------------------------------------------------- basic vector kernels
@@ -1334,7 +1356,7 @@ static SolveResult bicgstab_persist(cfem_ctx* c, const Matrix& A, const double* 
     launch_pdl(k_bm_init, vec_grid(c, n), kBlock, 0, c->stream, n, b, v, A.dinv, r, rhat, p, c->partials, c->scalars, c->status, rtol2, atol2, make_fin(c));
     LAUNCHED(c); }
   SolveResult res{0, 0.0, false};
-  { ProfScope ps(c, PROF_SPMV);   // the whole loop is charged to the SpMV category of the breakdown
+  { ProfScope ps(c, PROF_SOLVER);   // one launch = the whole BiCGStab loop (its own category of the breakdown)
     launch_bicg_persist(c, A, rhat, x, r, p, v, t, rtol2, atol2, max_it); }
   poll_done(c, res);
   persist_comm_advance(c, 2 * (int64_t)res.iters, 3 * (int64_t)res.iters);

@@ -296,7 +296,8 @@ enum { CFEM_KERNEL_SPMV = 0, CFEM_KERNEL_ASM_RESIDUAL = 1, CFEM_KERNEL_ASM_JACOB
  *   0 SpMV  1 vector assembly  2 matrix assembly  3 Krylov vector kernels
  *   4 RV (stats + epsilon)     5 misc (gather/fill/axpy/bc)
  *   6 fused Chebyshev mass-solve iteration (SpMV + update)
- *   7 communication (halo pack + NCCL send/recv, all-reduce)            (arrays of 8) */
+ *   7 communication (halo pack + NCCL send/recv, all-reduce)
+ *   8 persistent BiCGStab kernel (one launch = one whole linear solve)  (arrays of 9) */
 int cfem_profile_begin(cfem_ctx* ctx, int max_launches);
 int cfem_profile_end(cfem_ctx* ctx, double* ms_per_category, int64_t* launches_per_category);
 /* L2 error against a P3 interpolant of the exact solution (f-2):  sqrt( int (uh - I3 u_ex)^2 dx ), the functional of

@@ -40,13 +40,20 @@ def launches(path, cmd):
     print("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| `{k}` | {n} | {t:.1f} | {t / n:.1f} | {100 * t / tot:.1f}% |")
-    sp = sum(t for k, (n, t) in agg.items() if "k_spmv_stream" in k or "k_cheb_stream" in k)
-    ch = sum(t for k, (n, t) in agg.items() if "k_cheb_stream" in k)
-    print(f"\nSpMV-type kernels (k_spmv_stream + k_cheb_stream): {100 * sp / tot:.1f}% of the captured time; k_cheb_stream alone {100 * ch / tot:.1f}%.")
+    def share(pred):
+        return 100 * sum(t for k, (n, t) in agg.items() if pred(k)) / tot
+    print(f"\nGroups: persistent BiCGStab (k_bicg_persist) {share(lambda k: 'k_bicg_persist' in k):.1f}%; "
+          f"Chebyshev mass sweeps (k_tile_t16<Ep16Cheb..>, k_cheb_stream) {share(lambda k: 'Cheb' in k or 'k_cheb' in k):.1f}%; "
+          f"other SpMV (k_tile_t16<Ep16Spmv/BiT>, k_spmv_stream) {share(lambda k: ('k_tile_t16' in k and 'Cheb' not in k) or 'k_spmv_stream' in k):.1f}%; "
+          f"assembly (k_tile_assemble) {share(lambda k: 'k_tile_assemble' in k):.1f}%; "
+          f"epsilon/statistics (k_epsilon*, k_stats*) {share(lambda k: 'k_epsilon' in k or 'k_stats' in k):.1f}%.")
 
 
 FULL = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lts__t_sectors_srcunit_tex.sum",
+        "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
