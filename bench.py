@@ -231,11 +231,21 @@ def run_euler(args, device):
     ctx.profile_begin(400000)
     ctx.step_euler(p, K)
     prof = ctx.profile_end()
-    t0 = time.perf_counter()
-    for _ in range(min(K, 5)):   # end to end: (Nn,4) host state up, one step, state back
-        ctx.euler_state_set(Uh=U0, Un=U0, Uold=U0, Uoo=U0, t=0.0)
+    # end to end: the (Nn,4) state history lives in PINNED host arrays; per step it goes up, one step runs, Uh comes back
+    pin = {k: torch.empty((nn, 4), dtype=torch.float64, pin_memory=True) for k in ("Uh", "Un", "Uold", "Uoo", "out")}
+    hv = {k: v.numpy() for k, v in pin.items()}
+    for k in ("Uh", "Un", "Uold", "Uoo"):
+        hv[k][:] = U0
+
+    def e2e_step():
+        ctx.euler_state_set(Uh=hv["Uh"], Un=hv["Un"], Uold=hv["Uold"], Uoo=hv["Uoo"], t=0.0)
         ctx.step_euler(p, 1)
-        ctx.euler_state_get(("Uh",))
+        ctx.euler_state_get(("Uh",), out={"Uh": hv["out"]})
+
+    e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(min(K, 5)):
+        e2e_step()
     e2e_s = (time.perf_counter() - t0) / min(K, 5)
     # roofline of the dominant kernel, k_apply4 (matrix-free 4-component Jacobian / residual apply, thread per row):
     # algorithmic bytes of one Jacobian-vector product = three scalar CSR value arrays + the shared pattern, three
@@ -413,7 +423,22 @@ def main():
         dev_ms = float(t.item())
     value = nn * K / (dev_ms * 1e-3)
 
+    # whole-solve timings of THIS context (un-profiled, collective): one event pair around a fixed-length solve, so
+    # the figures are comparable between GPU counts -- they split a step's growth into "mass solve", "Krylov solve"
+    # and "everything else"
+    def solve_timing():
+        ms_m, _ = ctx.time_kernel(L.KERNEL_CHEB_ITER, p.flux, reps=3)
+        ms_k, _ = ctx.time_kernel(L.KERNEL_KRYLOV_ITER, p.flux, reps=3)
+        out = {"mass_solve_24_iterations_ms": ms_m, "mass_us_per_iteration": 1e3 * ms_m / 24,
+               "krylov_solve_16_iterations_ms": ms_k, "krylov_us_per_iteration": 1e3 * ms_k / 16}
+        if dist is not None:
+            t = torch.tensor([ms_m, ms_k], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out["max_over_ranks"] = {"mass_solve_ms": float(t[0].item()), "krylov_solve_ms": float(t[1].item())}
+        return out
+
     if args.sweep:
+        solve_t = solve_timing()
         if rank == 0:
             print(json.dumps({
                 "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -425,6 +450,7 @@ def main():
                            "krylov_its_per_step": st["krylov_iterations"] / K,
                            "mass_its_per_step": st["mass_iterations"] / K,
                            "comm": ctx.comm_stats() if world > 1 else None, "comm_wait": comm_wait,
+                           "solve_timing": solve_t,
                            "n_ghosts_rank0": ctx.n_ghosts, "device_bytes_rank0": ctx.device_bytes,
                            "mesh_generation_s": t_mesh, "context_setup_s_rank0": t_ctx},
                 "parity_rel_l2": parity, "gpu_launches": int(st["kernel_launches"]), "clocks": clk.summary()}))
@@ -456,6 +482,7 @@ def main():
     # such runs inside the step (one per mass solve: ~24 launches); stand-alone SpMVs alternate with other kernels,
     # so their run is a separate chain of 20 launches on the step's last Jacobian (cfem_time_kernel).
     spmv_chain_ms, _ = ctx.time_kernel(L.KERNEL_SPMV_SYSTEM, p.flux, reps=20)
+    solve_t = solve_timing()
     per_launch = {"chebyshev": prof["chebyshev"]["ms"] / max(prof["chebyshev"]["launches"], 1), "spmv": spmv_chain_ms}
     if prof["solver"]["launches"]:
         # the whole-solve kernel: event pair around each launch (it IS the run), bytes = iterations it ran x per-iteration
@@ -583,7 +610,7 @@ def main():
                        "layer; data plane = stores into the neighbours' CUDA-IPC mailboxes over NVLink from inside the SpMV-type "
                        "kernels (halo) and tagged-word all-reduce kernels; NCCL only for set-up (handle exchange) and as the "
                        "CFEM_COMM=nccl fallback"),
-                   "comm": ctx.comm_stats() if world > 1 else None, "comm_wait": comm_wait, "tiles": ctx.num_tiles,
+                   "comm": ctx.comm_stats() if world > 1 else None, "comm_wait": comm_wait, "solve_timing": solve_t, "tiles": ctx.num_tiles,
                    "l2": "no flush between steps: a step streams 3 matrices (2 x 59 MB values + 21 MB pattern) and ~30 nodal vectors "
                          "(8.4 MB each) = ~400 MB > the 126 MB L2, so every step starts with cold lines; WITHIN a solve the matrix is "
                          "deliberately kept L2-resident (persisting access-policy window)",

@@ -23,7 +23,7 @@ SOLVER_PCG, SOLVER_BICGSTAB, SOLVER_GMRES, SOLVER_CHEBYSHEV = 0, 1, 2, 3
 BC_CONSTANT, BC_BURGERS_EXACT, BC_USER = 0, 1, 2
 ORDER_HILBERT, ORDER_NATURAL = 0, 1
 KERNEL_SPMV, KERNEL_ASM_RESIDUAL, KERNEL_ASM_JACOBIAN, KERNEL_RV_EPSILON, KERNEL_ASM_RV_RHS = 0, 1, 2, 3, 4
-KERNEL_COMM_ALLREDUCE, KERNEL_COMM_HALO, KERNEL_SPMV_SYSTEM, KERNEL_CHEB_ITER = 6, 7, 8, 9
+KERNEL_COMM_ALLREDUCE, KERNEL_COMM_HALO, KERNEL_SPMV_SYSTEM, KERNEL_CHEB_ITER, KERNEL_KRYLOV_ITER = 6, 7, 8, 9, 10
 
 FLUX_BY_NAME = {"advection": FLUX_ADVECTION, "burgers": FLUX_BURGERS, "kpp": FLUX_KPP}
 SOLVER_BY_NAME = {"pcg": SOLVER_PCG, "bicgstab": SOLVER_BICGSTAB, "gmres": SOLVER_GMRES, "chebyshev": SOLVER_CHEBYSHEV}

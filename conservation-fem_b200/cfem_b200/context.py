@@ -328,11 +328,22 @@ class Context:
         hh = _field(h)
         L.check(self._lib.cfem_euler_state_set(self._h, *[L.ptr(a) for a in args], L.ptr(hh), float(t)))
 
-    def euler_state_get(self, want=("Uh",)):
+    def euler_state_get(self, want=("Uh",), out=None):
+        """``out``: optional dict of caller arrays to fill (e.g. pinned buffers), keyed like ``want``."""
+        given = out or {}
         out = {}
-        Uh = np.zeros((self.n, 4)) if "Uh" in want else None
-        R = np.zeros((self.n, 4)) if "R" in want else None
-        eps = np.zeros(self.n) if "eps" in want else None
+
+        def buf(key, shape):
+            if key not in want:
+                return None
+            a = given.get(key)
+            if a is None:
+                return np.zeros(shape)
+            if a.dtype != np.float64 or not a.flags.c_contiguous or a.shape != shape:
+                raise ValueError(f"euler_state_get: out[{key!r}] must be a C-contiguous float64 array of shape {shape}")
+            return a
+
+        Uh, R, eps = buf("Uh", (self.n, 4)), buf("R", (self.n, 4)), buf("eps", (self.n,))
         t = C.c_double(0.0)
         L.check(self._lib.cfem_euler_state_get(self._h, L.ptr(Uh), L.ptr(R), L.ptr(eps), C.byref(t)))
         for k, v in (("Uh", Uh), ("R", R), ("eps", eps)):

@@ -1022,8 +1022,23 @@ int cfem_profile_end(cfem_ctx* c, double* ms_per_category, int64_t* launches_per
 
 // ---- Euler system ---------------------------------------------
 // (Nn,4) caller arrays <-> local AoS device vectors; host staging through pageable copies.
+// One GPU: the caller's array goes to the device as it is (one copy at PCIe speed from pinned memory) and is permuted
+// there; distributed contexts gather their own entries on the host and ship only those.
+static double* stage4(cfem_ctx* c) {
+  if (!c->stage4) c->stage4 = dalloc<double>(c, 4 * c->dm.nn);
+  return c->stage4;
+}
 static void import_vec4(cfem_ctx* c, const double* user, double* dst) {
   const int64_t nl = c->dm.nn;
+  if (c->world == 1) {
+    const double* src = user;
+    if (!is_device_ptr(user)) {
+      CUDA_OK(cudaMemcpyAsync(stage4(c), user, 4 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      src = stage4(c);
+    }
+    launch_gather4(c, (const double4*)src, c->d_n2u, (double4*)dst, nl);
+    return;
+  }
   std::vector<double> tmp;
   const double* src = user;
   std::vector<double> host_copy;
@@ -1042,11 +1057,17 @@ static void import_vec4(cfem_ctx* c, const double* user, double* dst) {
   CUDA_OK(cudaMemcpy(dst, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
 }
 static void export_vec4(cfem_ctx* c, const double* internal, double* user) {
+  if (is_device_ptr(user)) CFEM_THROW(-1, "euler_state_get: outputs must be host arrays");
   const int64_t no = c->dm.no;
+  if (c->world == 1) {
+    launch_gather4(c, (const double4*)internal, c->d_u2n, (double4*)stage4(c), no);
+    CUDA_OK(cudaMemcpyAsync(user, stage4(c), 4 * (size_t)no * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return;
+  }
   std::vector<double> tmp(4 * (size_t)no);
   CUDA_OK(cudaStreamSynchronize(c->stream));
   CUDA_OK(cudaMemcpy(tmp.data(), internal, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  if (is_device_ptr(user)) CFEM_THROW(-1, "euler_state_get: outputs must be host arrays");
   const int32_t* n2u = c->hm.n2u.data();
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < no; ++i)
@@ -1182,6 +1203,18 @@ int cfem_time_kernel(cfem_ctx* c, int kernel, int flux, int reps, double* ms_per
         allreduce_partials(c, 3, sl, op, 1184);
         bytes = 24.0 * c->world; break; }
       case CFEM_KERNEL_COMM_HALO: halo_exchange(c, c->u_n, 1); bytes = 8.0 * (double)(c->dm.nn - c->dm.no); break;
+      case CFEM_KERNEL_CHEB_ITER: {
+        // a whole mass solve of exactly 24 iterations (tolerance 0: no early exit; one norm check at the end), as the
+        // residual projection of a step runs it -- collective in a distributed context.  Reported per iteration.
+        int predict = 24;
+        chebyshev_mass(c, M, c->u_n, c->wk[9], 0.0, 24, &predict);
+        bytes = 24.0 * (12.0 * nnz + 4.0 * (nn + 1) + 48.0 * nn); break; }
+      case CFEM_KERNEL_KRYLOV_ITER: {
+        // a whole BiCGStab solve of exactly 16 iterations on the current system matrix (tolerances 0), collective
+        if (!J.valid) CFEM_THROW(-1, "time_kernel: no system matrix assembled yet");
+        launch_fill(c, c->wk[9], 0.0, c->dm.nn);
+        bicgstab(c, J, c->u_n, c->wk[9], 0.0, 0.0, 16, nullptr);
+        bytes = 16.0 * (24.0 * nnz + 8.0 * (nn + 1) + 136.0 * nn); break; }
       default: CFEM_THROW(-1, "time_kernel: unknown kernel id");
     }
   };

@@ -173,6 +173,7 @@ struct cfem_ctx {
   // work vectors
   double *wk[10] = {nullptr};
   double *stage[4] = {nullptr};   // staging for host<->device + permutation
+  double* stage4 = nullptr;       // 4 * nn doubles, allocated on first use (Euler state import / export on one GPU)
   double *partials = nullptr;     // 8 * kMaxPartials doubles
   double *partials12 = nullptr;   // 12 more slots (Euler: sum/min/max of 4 components)
   double* gmres_V = nullptr;      // lazily allocated Krylov basis (31 vectors) and small dense block

@@ -45,6 +45,7 @@ void launch_spmv_dots2(cfem_ctx* c, const Matrix& A, const double* x, double* y,
 void launch_gather(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n);      // dst[i] = src[idx[i]]
 void launch_scatter(cfem_ctx* c, const double* src, const int32_t* idx, double* dst, int64_t n);     // dst[idx[i]] = src[i]
 void launch_gather2(cfem_ctx* c, const double2* src, const int32_t* idx, double2* dst, int64_t n);
+void launch_gather4(cfem_ctx* c, const double4* src, const int32_t* idx, double4* dst, int64_t n);
 void launch_fill(cfem_ctx* c, double* dst, double v, int64_t n);
 void launch_copy(cfem_ctx* c, double* dst, const double* src, int64_t n);
 // dst[idx[k]] = src[idx[k]], k < n

@@ -111,6 +111,9 @@ __global__ void k_gather(const double* __restrict__ src, const int32_t* __restri
 __global__ void k_gather2(const double2* __restrict__ src, const int32_t* __restrict__ idx, double2* __restrict__ dst, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) dst[i] = src[idx[i]];
 }
+__global__ void k_gather4(const double4* __restrict__ src, const int32_t* __restrict__ idx, double4* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) dst[i] = src[idx[i]];
+}
 __global__ void k_fill(double* __restrict__ dst, double v, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) dst[i] = v;
 }
@@ -146,6 +149,10 @@ void launch_gather(cfem_ctx* c, const double* src, const int32_t* idx, double* d
 void launch_gather2(cfem_ctx* c, const double2* src, const int32_t* idx, double2* dst, int64_t n) {
   ProfScope ps(c, PROF_MISC);
   k_gather2<<<vec_grid(c, n), kBlock, 0, c->stream>>>(src, idx, dst, n); LAUNCHED(c);
+}
+void launch_gather4(cfem_ctx* c, const double4* src, const int32_t* idx, double4* dst, int64_t n) {
+  ProfScope ps(c, PROF_MISC);
+  k_gather4<<<vec_grid(c, n), kBlock, 0, c->stream>>>(src, idx, dst, n); LAUNCHED(c);
 }
 void launch_fill(cfem_ctx* c, double* dst, double v, int64_t n) {
   ProfScope ps(c, PROF_MISC);
@@ -290,6 +297,9 @@ k_spmv_stream(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__
 #ifndef CFEM_T16_MINB
 #define CFEM_T16_MINB 6   // resident CTAs per SM the register budget is held to (<= 42 registers)
 #endif
+#ifndef CFEM_T16_MINB_GHOST
+#define CFEM_T16_MINB_GHOST CFEM_T16_MINB   // the distributed variants (ghost columns, halo words)
+#endif
 struct EpPre { double a, b, c; };
 
 template <int NDOT>
@@ -386,7 +396,7 @@ struct Ep16Cheb {  // one Chebyshev iteration of the mass solve: r = b - M x, z 
 };
 
 template <class EP, bool GHOST>
-__global__ void __launch_bounds__(kTileNodes, CFEM_T16_MINB)
+__global__ void __launch_bounds__(kTileNodes, GHOST ? CFEM_T16_MINB_GHOST : CFEM_T16_MINB)
 k_tile_t16(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ tile_order, const int n_interior,
            const int ntiles, const int32_t* __restrict__ tile_node, const int32_t* __restrict__ rowptr,
            const uint16_t* __restrict__ lc16, const int32_t* __restrict__ extptr, const int32_t* __restrict__ ext,

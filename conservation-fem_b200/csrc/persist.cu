@@ -31,6 +31,15 @@
 
 namespace cfem {
 
+// The two words of the grid barrier live 256 bytes apart (different L2 slices: the address hash starts at bit 8): the
+// arrival atomics of the late CTAs -- the critical path -- do not queue behind the polls of the early ones.
+#ifndef CFEM_BAR_GEN
+#define CFEM_BAR_GEN 64      // index (in 32-bit words) of the generation word; the arrival counter is word 0
+#endif
+#ifndef CFEM_BAR_BACKOFF
+#define CFEM_BAR_BACKOFF 0   // ns of __nanosleep between polls of the generation word (0: none)
+#endif
+
 #ifndef CFEM_PERSIST_MINB
 #define CFEM_PERSIST_MINB 4   // 64 registers: no spills; measured 2.58 vs 2.76 (5 CTAs, 48 regs, spills) vs 2.85 ms per step (6 CTAs)
 #endif
@@ -115,12 +124,13 @@ __device__ __forceinline__ void grid_reduce(const BicgArgs& a, const int nblk, c
     if (threadIdx.x == 0) {
       a.bar[0] = 0;
       __threadfence();
-      atomicExch(a.bar + 1, gen);   // release
+      atomicExch(a.bar + CFEM_BAR_GEN, gen);   // release
     }
   } else {
     if (threadIdx.x == 0) {
       const long long t0 = clock64();
-      while ((int)(ld_acquire_u32(a.bar + 1) - gen) < 0) {
+      while ((int)(ld_acquire_u32(a.bar + CFEM_BAR_GEN) - gen) < 0) {
+        if (CFEM_BAR_BACKOFF) __nanosleep(CFEM_BAR_BACKOFF);
         // bounded (~10 s): raise the flag and fall through; once it is up every later barrier falls through at once
         if (clock64() - t0 > 20000000000LL || *(volatile int32_t*)(a.status + 3)) {
           a.status[3] = 1;
@@ -375,10 +385,11 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, int32_t* status, in
     if (t == (unsigned int)nblk - 1u) {
       bar[0] = 0;
       __threadfence();
-      atomicExch(bar + 1, gen);
+      atomicExch(bar + CFEM_BAR_GEN, gen);
     } else {
       const long long t0 = clock64();
-      while ((int)(ld_acquire_u32(bar + 1) - gen) < 0) {
+      while ((int)(ld_acquire_u32(bar + CFEM_BAR_GEN) - gen) < 0) {
+        if (CFEM_BAR_BACKOFF) __nanosleep(CFEM_BAR_BACKOFF);
         if (clock64() - t0 > 20000000000LL || *(volatile int32_t*)(status + 3)) {
           status[3] = 1;
           if (error) *error = 1;
@@ -502,7 +513,8 @@ k_cheb_persist(const ChebArgs a) {
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
-struct PersistPlan { int grid = 0, grid_cheb = 0; size_t smem = 0; bool ok = false, tried = false, ghost = false; };
+constexpr size_t kBarBytes = 512;
+struct PersistPlan { int grid = 0, grid_cheb = 0; size_t smem = 0; bool ok = false, tried = false, ghost = false; unsigned int* bar = nullptr; };
 
 template <class K>
 static int plan_kernel(cfem_ctx* c, K kern, size_t smem, bool ghost) {
@@ -534,6 +546,7 @@ static bool persist_plan(cfem_ctx* c) {
       pl->grid_cheb = pl->ghost ? plan_kernel(c, k_cheb_persist<true>, pl->smem, true) : plan_kernel(c, k_cheb_persist<false>, pl->smem, false);
     }
     pl->ok = pl->grid > 0 && pl->grid_cheb > 0 && (c->world == 1 || c->p2p != nullptr);
+    if (pl->ok && cudaMalloc((void**)&pl->bar, kBarBytes) != cudaSuccess) { cudaGetLastError(); pl->bar = nullptr; pl->ok = false; }
   }
   return pl->ok;
 }
@@ -552,6 +565,7 @@ bool cheb_persist_available(cfem_ctx* c) {
 }
 
 void persist_plan_free(cfem_ctx* c) {
+  if (c->persist_plan && ((PersistPlan*)c->persist_plan)->bar) cudaFree(((PersistPlan*)c->persist_plan)->bar);
   delete (PersistPlan*)c->persist_plan;
   c->persist_plan = nullptr;
 }
@@ -569,9 +583,10 @@ void launch_bicg_persist(cfem_ctx* c, const Matrix& A, const double* rhat, doubl
   a.vals = A.vals; a.dinv = A.dinv; a.rhat = rhat;
   a.x = x; a.r = r; a.p = p; a.v = v; a.t = t;
   a.part = c->partials; a.scalars = c->scalars; a.status = c->status;
-  a.bar = (unsigned int*)(c->status + 5);
+  a.bar = pl->bar;
   a.rtol2 = rtol2; a.atol2 = atol2; a.max_it = max_it;
-  CUDA_OK(cudaMemsetAsync(c->status + 3, 0, 4 * sizeof(int32_t), c->stream));   // time-out flag, fin ticket, barrier words
+  CUDA_OK(cudaMemsetAsync(c->status + 3, 0, 2 * sizeof(int32_t), c->stream));   // time-out flag, fin ticket
+  CUDA_OK(cudaMemsetAsync(pl->bar, 0, kBarBytes, c->stream));                    // barrier words
   persist_comm_args(c, &a.dev, &a.mailbox, &a.halo_off, &a.halo_stride, &a.peer_rank, &a.npeer, &a.error, &a.halo_seq0, &a.red_seq0, &a.tim);
   void* args[] = {(void*)&a};
   if (pl->ghost)
@@ -595,10 +610,11 @@ void launch_cheb_persist(cfem_ctx* c, const Matrix& A, const double* b, double* 
   a.vals = A.vals; a.dinv = A.dinv; a.b = b;
   a.x0 = x_in; a.x1 = x_other; a.d = d;
   a.part = c->partials; a.scalars = c->scalars; a.status = c->status;
-  a.bar = (unsigned int*)(c->status + 5);
+  a.bar = pl->bar;
   a.first = first ? 1 : 0; a.iters = iters;
   a.rho0 = rho0; a.sigma1 = sigma1; a.theta = theta; a.delta = delta;
-  CUDA_OK(cudaMemsetAsync(c->status + 3, 0, 4 * sizeof(int32_t), c->stream));
+  CUDA_OK(cudaMemsetAsync(c->status + 3, 0, 2 * sizeof(int32_t), c->stream));
+  CUDA_OK(cudaMemsetAsync(pl->bar, 0, kBarBytes, c->stream));
   persist_comm_args(c, &a.dev, &a.mailbox, &a.halo_off, &a.halo_stride, &a.peer_rank, &a.npeer, &a.error, &a.halo_seq0, &a.red_seq0, &a.tim);
   void* args[] = {(void*)&a};
   if (pl->ghost)

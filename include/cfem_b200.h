@@ -289,7 +289,8 @@ enum { CFEM_KERNEL_SPMV = 0, CFEM_KERNEL_ASM_RESIDUAL = 1, CFEM_KERNEL_ASM_JACOB
        CFEM_KERNEL_RV_EPSILON = 3, CFEM_KERNEL_ASM_RV_RHS = 4, CFEM_KERNEL_PCG_ITER = 5,
        CFEM_KERNEL_COMM_ALLREDUCE = 6 /* 3-scalar all-reduce over the ranks */, CFEM_KERNEL_COMM_HALO = 7 /* full halo exchange of one field */,
        CFEM_KERNEL_SPMV_SYSTEM = 8 /* SpMV with two fused dots on CFEM_MAT_SYSTEM (the BiCGStab kernel) */,
-       CFEM_KERNEL_CHEB_ITER = 9 /* one Chebyshev iteration on CFEM_MAT_MASS_BC */ };
+       CFEM_KERNEL_CHEB_ITER = 9 /* a 24-iteration Chebyshev mass solve on CFEM_MAT_MASS_BC (one "launch" = the solve) */,
+       CFEM_KERNEL_KRYLOV_ITER = 10 /* a 16-iteration BiCGStab solve on CFEM_MAT_SYSTEM (one "launch" = the solve) */ };
 /* Bracket every kernel launch of the following calls with CUDA events (adds ~2 us
  * per launch; use on a separate pass, not on the timed one).  cfem_profile_end sums
  * the device time and launch count per category:

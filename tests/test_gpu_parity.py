@@ -400,6 +400,23 @@ def test_euler_steps():
         assert U[:, 0].min() > 0.1 and np.all(np.isfinite(U))
 
 
+def test_euler_state_round_trip_into_caller_buffers():
+    """cfem_euler_state_set / _get move the (Nn,4) state through the device in the caller's numbering: what goes in
+    comes out to the bit, also into caller-provided (e.g. pinned) output arrays."""
+    x, c = meshes.jittered(21, 13, (0, 0), (2, 1))
+    ctx = Context((x, c))
+    rng = np.random.default_rng(3)
+    U = rng.normal(size=(ctx.n, 4))
+    ctx.euler_state_set(Uh=U, Un=U, Uold=U, Uoo=U, bc_state=U, h=ctx.nodal_h(), t=0.25)
+    got = ctx.euler_state_get(("Uh",))
+    assert np.array_equal(got["Uh"], U) and got["t"] == 0.25
+    buf = np.full((ctx.n, 4), np.nan)
+    got = ctx.euler_state_get(("Uh",), out={"Uh": buf})
+    assert got["Uh"] is buf and np.array_equal(buf, U)
+    with pytest.raises(ValueError):
+        ctx.euler_state_get(("Uh",), out={"Uh": np.zeros((ctx.n, 3))})
+
+
 def test_determinism_bitwise():
     """Atomics-free assembly and fixed-order reductions: two runs agree bit for bit."""
     x, c = meshes.jittered(32, 32, (-2, -2), (2, 2))
