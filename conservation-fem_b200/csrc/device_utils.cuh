@@ -110,13 +110,13 @@ __device__ __forceinline__ int round_of(const int kk, const int nrounds) {
   return kk == mid ? nrounds - 1 : (kk > mid ? kk - 1 : kk);
 }
 
-template <bool GHOST>
+template <bool GHOST, bool MID = GHOST>
 __device__ __forceinline__ TileMeta tile_meta_of(const int kk, const int nrounds, const int wid, const int nwork,
                                                  const int ntiles, const int32_t* __restrict__ tile_order,
                                                  const int32_t* __restrict__ tile_node, const int32_t* __restrict__ extptr,
                                                  const int32_t* __restrict__ rowptr) {
   TileMeta m;
-  m.t = wid + round_of<GHOST>(kk, nrounds) * nwork;
+  m.t = wid + round_of<MID>(kk, nrounds) * nwork;
   if (m.t >= ntiles) { m.t = -1; m.n0 = m.nrows = m.e0 = m.ne = m.start = m.cnt = 0; return m; }
   const int tile = GHOST ? tile_order[m.t] : m.t;
   m.n0 = tile_node[tile];
@@ -129,13 +129,13 @@ __device__ __forceinline__ TileMeta tile_meta_of(const int kk, const int nrounds
 }
 
 // all threads of the CTA; smeta: kMetaRounds entries of shared memory; followed by a __syncthreads() of the caller
-template <bool GHOST>
+template <bool GHOST, bool MID = GHOST>
 __device__ __forceinline__ void fetch_tile_meta(TileMeta* smeta, const int nrounds, const int wid, const int nwork,
                                                 const int ntiles, const int32_t* __restrict__ tile_order,
                                                 const int32_t* __restrict__ tile_node, const int32_t* __restrict__ extptr,
                                                 const int32_t* __restrict__ rowptr) {
   if (nrounds <= kMetaRounds && (int)threadIdx.x < nrounds)
-    smeta[threadIdx.x] = tile_meta_of<GHOST>(threadIdx.x, nrounds, wid, nwork, ntiles, tile_order, tile_node, extptr, rowptr);
+    smeta[threadIdx.x] = tile_meta_of<GHOST, MID>(threadIdx.x, nrounds, wid, nwork, ntiles, tile_order, tile_node, extptr, rowptr);
 }
 
 struct CellGeom {

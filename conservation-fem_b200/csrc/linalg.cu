@@ -395,6 +395,79 @@ struct Ep16Cheb {  // one Chebyshev iteration of the mass solve: r = b - M x, z 
   }
 };
 
+// One tile of a staged tile kernel.  GH: the tile has ghost columns (a boundary tile of a distributed context); the
+// interior-tile instance carries none of the mailbox code, so the distributed kernels run their interior tiles --
+// 95 % of them at 1 M rows per GPU -- through the same instruction stream as the one-GPU kernels.  Returns false when
+// the launch is gated off (a predecessor raised the status flag).
+template <class EP, bool GH>
+__device__ __forceinline__ bool t16_tile(const TileMeta& tm, const GhostSrc& gsrc, const int64_t no,
+                                         const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ lc16,
+                                         const int32_t* __restrict__ ext, const double* __restrict__ vals,
+                                         const double* __restrict__ x, const EP& ep, const int32_t* __restrict__ status,
+                                         double* const prod, double* const xs, int32_t* const rp, double* acc,
+                                         bool& synced, bool& waited) {
+  const int tid = threadIdx.x;
+  const int n0 = tm.n0, nrows = tm.nrows, e0 = tm.e0, ne = tm.ne, start = tm.start, cnt = tm.cnt;
+  for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i] - start;
+  const double* __restrict__ v = vals + start;
+  const uint16_t* __restrict__ lc = lc16 + start;
+  // mesh tables only up to here (nothing a predecessor kernel writes), so under a programmatic launch these
+  // requests overlap the previous kernel's drain; the matrix values may come straight from an assembly kernel
+  const int ecol = tid < ne ? ext[e0 + tid] : 0;
+  int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+  if (tid < cnt) l0 = lc[tid];
+  if (tid + kTileNodes < cnt) l1 = lc[tid + kTileNodes];
+  if (tid + 2 * kTileNodes < cnt) l2 = lc[tid + 2 * kTileNodes];
+  if (tid + 3 * kTileNodes < cnt) l3 = lc[tid + 3 * kTileNodes];
+  if (!synced) {
+    pdl_wait();
+    pdl_launch();
+    synced = true;
+    if (status && status[0]) return false;
+  }
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  if (tid < cnt) v0 = v[tid];
+  if (tid + kTileNodes < cnt) v1 = v[tid + kTileNodes];
+  if (tid + 2 * kTileNodes < cnt) v2 = v[tid + 2 * kTileNodes];
+  if (tid + 3 * kTileNodes < cnt) v3 = v[tid + 3 * kTileNodes];
+  if (GH && !waited) { if (!gsrc.ll) ghost_wait(gsrc); waited = true; }
+  // ---- stage x: own rows, then the external columns
+  double xown = 0.0;
+  if (tid < nrows) { xown = x[n0 + tid]; xs[tid] = xown; }
+  if (!GH) {
+    if (tid < ne) xs[kTileNodes + tid] = x[ecol];
+    for (int e = tid + kTileNodes; e < ne; e += kTileNodes) xs[kTileNodes + e] = x[ext[e0 + e]];
+  } else {
+    const double* const mbox_shifted = gsrc.mbox - no;  // mbox_shifted[col] == mailbox[col - no]
+    if (tid < ne) xs[kTileNodes + tid] = ecol >= no ? ghost_value(gsrc, mbox_shifted, ecol, no) : x[ecol];
+    for (int e = tid + kTileNodes; e < ne; e += kTileNodes) {
+      const int cc = ext[e0 + e];
+      xs[kTileNodes + e] = cc >= no ? ghost_value(gsrc, mbox_shifted, cc, no) : x[cc];
+    }
+  }
+  EpPre q{0.0, 0.0, 0.0};
+  if (tid < nrows) q = ep.pre(n0 + tid);   // epilogue operands requested before the barrier
+  __syncthreads();
+  // ---- products
+  {
+    const int p = tid;
+    if (p < cnt) prod[p] = v0 * xs[l0];
+    if (p + kTileNodes < cnt) prod[p + kTileNodes] = v1 * xs[l1];
+    if (p + 2 * kTileNodes < cnt) prod[p + 2 * kTileNodes] = v2 * xs[l2];
+    if (p + 3 * kTileNodes < cnt) prod[p + 3 * kTileNodes] = v3 * xs[l3];
+  }
+  for (int p = tid + 4 * kTileNodes; p < cnt; p += kTileNodes) prod[p] = v[p] * xs[lc[p]];
+  __syncthreads();
+  if (tid < nrows) {
+    const int a = rp[tid], b = rp[tid + 1];
+    double s = 0.0;
+    for (int k = a; k < b; ++k) s += prod[k];
+    ep.row(n0 + tid, s, xown, q, acc);
+  }
+  __syncthreads();
+  return true;
+}
+
 template <class EP, bool GHOST>
 __global__ void __launch_bounds__(kTileNodes, GHOST ? CFEM_T16_MINB_GHOST : CFEM_T16_MINB)
 k_tile_t16(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ tile_order, const int n_interior,
@@ -418,66 +491,29 @@ k_tile_t16(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ ti
 #pragma unroll
   for (int k = 0; k < NA; ++k) acc[k] = 0.0;
   bool waited = false, synced = false;
-  const double* const mbox_shifted = GHOST ? gsrc.mbox - no : nullptr;  // mbox_shifted[col] == mailbox[col - no]
   if (bid >= ntiles) { pdl_wait(); pdl_launch(); }
-  // the CTA's tile schedule, resolved once (mesh tables only: overlaps the previous kernel's drain)
+  // the CTA's tile schedule, resolved once (mesh tables only: overlaps the previous kernel's drain).  Rounds in
+  // tile_order: the interior tiles first, a CTA's boundary tiles (if any) in its last rounds -- by then the
+  // neighbours' halo values, pushed at the start of the kernel, have arrived.
   __shared__ TileMeta smeta[kMetaRounds];
   const int nrounds = (ntiles + nblk - 1) / nblk;
-  fetch_tile_meta<GHOST>(smeta, nrounds, bid, nblk, ntiles, tile_order, tile_node, extptr, rowptr);
+  fetch_tile_meta<GHOST, false>(smeta, nrounds, bid, nblk, ntiles, tile_order, tile_node, extptr, rowptr);
   __syncthreads();
-  for (int kk = 0; kk < nrounds; ++kk) {
+  int kk = 0;
+  for (; kk < nrounds; ++kk) {
     const TileMeta tm = nrounds <= kMetaRounds ? smeta[kk]
-                                               : tile_meta_of<GHOST>(kk, nrounds, bid, nblk, ntiles, tile_order, tile_node, extptr, rowptr);
+                                               : tile_meta_of<GHOST, false>(kk, nrounds, bid, nblk, ntiles, tile_order, tile_node, extptr, rowptr);
     if (tm.t < 0) continue;
-    const int t = tm.t, n0 = tm.n0, nrows = tm.nrows, e0 = tm.e0, ne = tm.ne, start = tm.start, cnt = tm.cnt;
-    for (int i = tid; i <= nrows; i += kTileNodes) rp[i] = rowptr[n0 + i] - start;
-    const double* __restrict__ v = vals + start;
-    const uint16_t* __restrict__ lc = lc16 + start;
-    // mesh tables only up to here (nothing a predecessor kernel writes), so under a programmatic launch these
-    // requests overlap the previous kernel's drain; the matrix values may come straight from an assembly kernel
-    const int ecol = tid < ne ? ext[e0 + tid] : 0;
-    int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-    if (tid < cnt) l0 = lc[tid];
-    if (tid + kTileNodes < cnt) l1 = lc[tid + kTileNodes];
-    if (tid + 2 * kTileNodes < cnt) l2 = lc[tid + 2 * kTileNodes];
-    if (tid + 3 * kTileNodes < cnt) l3 = lc[tid + 3 * kTileNodes];
-    if (!synced) {
-      pdl_wait();
-      pdl_launch();
-      synced = true;
-      if (status && status[0]) return;
+    if (GHOST && tm.t >= n_interior) break;
+    if (!t16_tile<EP, false>(tm, gsrc, no, rowptr, lc16, ext, vals, x, ep, status, prod, xs, rp, acc, synced, waited)) return;
+  }
+  if (GHOST) {
+    for (; kk < nrounds; ++kk) {
+      const TileMeta tm = nrounds <= kMetaRounds ? smeta[kk]
+                                                 : tile_meta_of<GHOST, false>(kk, nrounds, bid, nblk, ntiles, tile_order, tile_node, extptr, rowptr);
+      if (tm.t < 0) continue;
+      if (!t16_tile<EP, true>(tm, gsrc, no, rowptr, lc16, ext, vals, x, ep, status, prod, xs, rp, acc, synced, waited)) return;
     }
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-    if (tid < cnt) v0 = v[tid];
-    if (tid + kTileNodes < cnt) v1 = v[tid + kTileNodes];
-    if (tid + 2 * kTileNodes < cnt) v2 = v[tid + 2 * kTileNodes];
-    if (tid + 3 * kTileNodes < cnt) v3 = v[tid + 3 * kTileNodes];
-    if (GHOST && t >= n_interior && !waited) { if (!gsrc.ll) ghost_wait(gsrc); waited = true; }
-    // ---- stage x: own rows, then the external columns
-    double xown = 0.0;
-    if (tid < nrows) { xown = x[n0 + tid]; xs[tid] = xown; }
-    if (tid < ne) xs[kTileNodes + tid] = XG(x, ecol);
-    for (int e = tid + kTileNodes; e < ne; e += kTileNodes) { const int cc = ext[e0 + e]; xs[kTileNodes + e] = XG(x, cc); }
-    EpPre q{0.0, 0.0, 0.0};
-    if (tid < nrows) q = ep.pre(n0 + tid);   // epilogue operands requested before the barrier
-    __syncthreads();
-    // ---- products
-    {
-      const int p = tid;
-      if (p < cnt) prod[p] = v0 * xs[l0];
-      if (p + kTileNodes < cnt) prod[p + kTileNodes] = v1 * xs[l1];
-      if (p + 2 * kTileNodes < cnt) prod[p + 2 * kTileNodes] = v2 * xs[l2];
-      if (p + 3 * kTileNodes < cnt) prod[p + 3 * kTileNodes] = v3 * xs[l3];
-    }
-    for (int p = tid + 4 * kTileNodes; p < cnt; p += kTileNodes) prod[p] = v[p] * xs[lc[p]];
-    __syncthreads();
-    if (tid < nrows) {
-      const int a = rp[tid], b = rp[tid + 1];
-      double s = 0.0;
-      for (int k = a; k < b; ++k) s += prod[k];
-      ep.row(n0 + tid, s, xown, q, acc);
-    }
-    __syncthreads();
   }
   if (EP::NACC >= 1) {
     const Slots<NA> sl = ep.parts();
