@@ -461,6 +461,7 @@ def main():
     # ---- roofline leg: same K steps with every launch bracketed by CUDA events
     ctx.profile_begin(400000)
     stp = ctx.step_scalar(p, K)
+    gaps = ctx.profile_gaps()
     prof = ctx.profile_end()
     nnz = ctx.nnz        # of this rank's rows
     nn_rows = ctx.n_owned
@@ -526,7 +527,9 @@ def main():
                 "spmv_type_share_of_step": (prof["spmv"]["ms"] + prof["chebyshev"]["ms"] + prof["solver"]["ms"]) / total_prof_ms if total_prof_ms else None,
                 "per_kernel": other,
                 "breakdown_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
-                "launches_per_step": {k: v["launches"] / K for k, v in prof.items()}}
+                "launches_per_step": {k: v["launches"] / K for k, v in prof.items()},
+                "stream_idle_ms_per_step_after": {k: v / K for k, v in gaps.items()},
+                "profiled_leg_ms_per_step": stp["device_ms"] / K}
 
     # ---- end-to-end leg: fields live in pinned HOST memory, copied in and out every step
     def pinned(a):

@@ -112,6 +112,7 @@ SIGNATURES = {
     "cfem_step_advection": (_I, [_P, C.POINTER(StepParams), _I, _I, C.POINTER(StepStats)]),
     "cfem_step_scalar_si": (_I, [_P, C.POINTER(StepParams), _D, _D, _D, _P, _I, _P, C.POINTER(StepStats)]),
     "cfem_smooth_vector": (_I, [_P, _P, _P, _D]),
+    "cfem_profile_gaps": (_I, [_P, C.POINTER(_D)]),
     "cfem_euler_state_set": (_I, [_P, _P, _P, _P, _P, _P, _P, _D]),
     "cfem_euler_state_get": (_I, [_P, _P, _P, _P, C.POINTER(_D)]),
     "cfem_step_euler": (_I, [_P, C.POINTER(StepParams), _I, C.POINTER(StepStats)]),

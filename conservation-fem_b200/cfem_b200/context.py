@@ -367,6 +367,12 @@ class Context:
     def profile_begin(self, max_launches=200000):
         L.check(self._lib.cfem_profile_begin(self._h, int(max_launches)))
 
+    def profile_gaps(self):
+        """Stream idle time (ms) after the scopes of each category during the profiled calls; before profile_end."""
+        ms = (C.c_double * len(self.PROFILE_CATEGORIES))()
+        L.check(self._lib.cfem_profile_gaps(self._h, ms))
+        return {k: ms[i] for i, k in enumerate(self.PROFILE_CATEGORIES)}
+
     def profile_end(self):
         ms = (C.c_double * len(self.PROFILE_CATEGORIES))()
         cnt = (C.c_int64 * len(self.PROFILE_CATEGORIES))()

@@ -1020,6 +1020,22 @@ int cfem_profile_end(cfem_ctx* c, double* ms_per_category, int64_t* launches_per
   API_END
 }
 
+// Idle time of the stream BETWEEN the profiled scopes: gap_ms_after_category[k] = sum over consecutive scopes (a, b)
+// with a in category k of max(0, start(b) - end(a)).  Call before cfem_profile_end (which releases the records).
+int cfem_profile_gaps(cfem_ctx* c, double* gap_ms_after_category) {
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(c->device));
+  Profiler& p = c->prof;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < PROF_NCAT; ++k) gap_ms_after_category[k] = 0.0;
+  for (size_t e = 0; e + 3 < p.used; e += 2) {
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, p.ev[e + 1], p.ev[e + 2]));
+    if (ms > 0.f) gap_ms_after_category[p.cat[e / 2]] += ms;
+  }
+  API_END
+}
+
 // ---- Euler system ---------------------------------------------
 // (Nn,4) caller arrays <-> local AoS device vectors; host staging through pageable copies.
 // One GPU: the caller's array goes to the device as it is (one copy at PCIe speed from pinned memory) and is permuted

@@ -301,6 +301,9 @@ enum { CFEM_KERNEL_SPMV = 0, CFEM_KERNEL_ASM_RESIDUAL = 1, CFEM_KERNEL_ASM_JACOB
  *   8 persistent BiCGStab kernel (one launch = one whole linear solve)  (arrays of 9) */
 int cfem_profile_begin(cfem_ctx* ctx, int max_launches);
 int cfem_profile_end(cfem_ctx* ctx, double* ms_per_category, int64_t* launches_per_category);
+/* Stream idle time between consecutive profiled scopes, attributed to the category of the earlier one (array of 9);
+ * call before cfem_profile_end.  Host syncs and launch latency show up here, not in the per-category times. */
+int cfem_profile_gaps(cfem_ctx* ctx, double* gap_ms_after_category);
 /* L2 error against a P3 interpolant of the exact solution (f-2):  sqrt( int (uh - I3 u_ex)^2 dx ), the functional of
  * Code/Burgers_equation/Exact_Burger_RV_conv.py:81-86,223 and Code/Linear_advection/RV_node_convergence.py:49,69-70,239
  * (u_exact = Function(P3).interpolate(exact); assemble_scalar((uh - u_exact)**2 * dx)).  uh: P1 nodal values (NULL: the

@@ -17,7 +17,7 @@ try:
     d=json.loads(open(f+".json").read().strip().splitlines()[-1]); c=d["config"]
     its=(c.get("krylov_its_per_step"), c.get("mass_its_per_step") or c.get("mass_pcg_its_per_step"))
     print(f"{f.split('/')[-1]:28s} N={d['n_gpus']} {d['config']['workload'][:40]} cells {c['cells']} ms/step {d['ms_per_step']:.3f} value {d['value']/1e6:.1f}M its {its} setup {c.get('context_setup_s_rank0')} mesh {c.get('mesh_generation_s')}")
-    print("    parity", d.get("parity_rel_l2"), "\n    wait", c.get("comm_wait"))
+    print("    parity", d.get("parity_rel_l2"), "\n    wait", c.get("comm_wait"), "\n    solves", c.get("solve_timing"))
 except Exception as e:
     print(f, "FAILED", e); print(open(f+".err").read()[-1200:])
 PY
