@@ -415,7 +415,9 @@ def main():
                      "halo_waits_per_step": tm["halo_waits"] / K, "halo_wait_us_max": tm["halo_wait_us_max"],
                      "allreduce_us_per_step": tm["allreduce_us_total"] / K, "allreduces_per_step": tm["allreduces"] / K,
                      "allreduce_us_max": tm["allreduce_us_max"],
-                     "solver_barrier_us_per_step_worker0": tm["barrier_us_worker0"] / K, "solver_barriers_per_step": tm["barriers"] / K}
+                     "solver_barrier_us_per_step_worker0": tm["barrier_us_worker0"] / K, "solver_barriers_per_step": tm["barriers"] / K,
+                     "tile_kernel_halo_wait_us_per_boundary_tile": tm["tile_halo_wait_us_total"] / max(tm["tile_halo_waits"], 1),
+                     "tile_kernel_halo_waits_per_step": tm["tile_halo_waits"] / K, "tile_kernel_halo_wait_us_max": tm["tile_halo_wait_us_max"]}
     dev_ms = st["device_ms"]
     if dist is not None:
         t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")

@@ -417,10 +417,11 @@ class Context:
 
     def comm_timers(self, reset=True):
         """Device-measured waits of the peer-memory data plane since the last reset (microseconds / counts)."""
-        out = (C.c_double * 8)()
+        out = (C.c_double * 12)()
         L.check(self._lib.cfem_comm_timers(self._h, out, int(bool(reset))))
         k = ("halo_wait_us_total", "halo_waits", "halo_wait_us_max", "allreduce_us_total", "allreduces",
-             "allreduce_us_max", "barrier_us_worker0", "barriers")
+             "allreduce_us_max", "barrier_us_worker0", "barriers", "tile_halo_wait_us_total", "tile_halo_waits",
+             "tile_halo_wait_us_max", "reserved")
         return dict(zip(k, [float(v) for v in out]))
 
     def synchronize(self):

@@ -414,7 +414,7 @@ int cfem_comm_stats(const cfem_ctx* c, int64_t* halo_exchanges, int64_t* allredu
   return 0;
 }
 
-int cfem_comm_timers(cfem_ctx* c, double out[8], int reset) {
+int cfem_comm_timers(cfem_ctx* c, double out[12], int reset) {
   API_BEGIN
   CUDA_OK(cudaSetDevice(c->device));
   comm_timers(c, out, reset != 0);
@@ -843,9 +843,19 @@ static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps,
     static const bool fused_fj = !(getenv("CFEM_FUSED_FJ") && std::string(getenv("CFEM_FUSED_FJ")) == "0");
     int np = fused_fj ? launch_cn_residual_jacobian(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, fluxn, F, normpart, J)
                       : launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, fluxn, F, normpart);
-    double res = partials_norm(c, normpart, np);
-    const double res0 = res;
-    bool converged = res < p->newton_atol;
+    // ||F(u_0)||: the host needs it only to normalise the LATER residuals (and for the never-taken "already below
+    // atol" exit), so with in-kernel finished norms its copy is queued here and read after the first linear solve --
+    // one host round trip per step less (each one drains the stream and, distributed, exposes every rank's host
+    // jitter to all the others).  CFEM_SYNC_RES0=1 waits here as round 1 did.
+    static const bool sync_res0 = getenv("CFEM_SYNC_RES0") && std::string(getenv("CFEM_SYNC_RES0")) == "1";
+    const bool defer0 = fin_available(c) && !sync_res0;
+    double res = 0.0, res0 = 0.0;
+    if (defer0) {
+      CUDA_OK(cudaMemcpyAsync(c->h_pinned + 32, c->scalars + 24, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+      res = res0 = partials_norm(c, normpart, np);
+    }
+    bool converged = !defer0 && res < p->newton_atol;
     int it = 0;
     while (!converged && it < p->newton_max_it) {
       if (it > 0 || !fused_fj) launch_cn_jacobian(c, p->flux, p->dt, c->uh, c->eps, J);
@@ -861,6 +871,12 @@ static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps,
       // like the reference's LU does.
       launch_copy_indexed(c, dx, F, c->d_bc_nodes, c->nbc);
       SolveResult rk = run_solver(c, p->solver, J, F, dx, p->lin_rtol, 0.0, p->lin_max_it, &c->krylov_predict);
+      if (defer0 && it == 0) {
+        CUDA_OK(cudaStreamSynchronize(c->stream));   // the solver's own poll has already drained the stream
+        res = res0 = sqrt(c->h_pinned[32]);
+        // dolfinx takes no Newton step when the initial residual already meets atol: drop the update just computed
+        if (res0 < p->newton_atol) { converged = true; break; }
+      }
       if (!rk.converged) CFEM_THROW(-3, "step_scalar: Krylov solve did not converge (relres " + std::to_string(rk.relres) + ")");
       st.krylov_iterations += rk.iters;
       if (use_guess && it == 0) {

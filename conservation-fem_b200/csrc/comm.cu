@@ -411,8 +411,8 @@ static void p2p_setup(cfem_ctx* c) {
   CUDA_OK(cudaMalloc((void**)&d.counter, 2 * sizeof(unsigned int)));
   CUDA_OK(cudaMemset(d.counter, 0, 2 * sizeof(unsigned int)));
   c->allocs.push_back(d.counter);
-  CUDA_OK(cudaMalloc((void**)&d.tim, 8 * sizeof(unsigned long long)));
-  CUDA_OK(cudaMemset(d.tim, 0, 8 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMalloc((void**)&d.tim, 12 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMemset(d.tim, 0, 12 * sizeof(unsigned long long)));
   c->allocs.push_back(d.tim);
   CUDA_OK(cudaMallocHost((void**)&pp->h_error, sizeof(int)));
   *pp->h_error = 0;
@@ -635,18 +635,18 @@ void persist_comm_advance(cfem_ctx* c, int64_t halo_exchanges, int64_t allreduce
 }
 
 // cycles -> microseconds with the device's nominal SM clock; reset: start a new accounting interval
-void comm_timers(cfem_ctx* c, double* out8, bool reset) {
-  for (int k = 0; k < 8; ++k) out8[k] = 0.0;
+void comm_timers(cfem_ctx* c, double* out12, bool reset) {
+  for (int k = 0; k < 12; ++k) out12[k] = 0.0;
   if (c->world == 1 || !c->p2p) return;
   P2P* pp = (P2P*)c->p2p;
-  unsigned long long h[8];
+  unsigned long long h[12];
   CUDA_OK(cudaStreamSynchronize(c->stream));
   CUDA_OK(cudaMemcpy(h, pp->d.tim, sizeof(h), cudaMemcpyDeviceToHost));
   if (reset) CUDA_OK(cudaMemset(pp->d.tim, 0, sizeof(h)));
   int khz = 0;
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
   const double us = khz > 0 ? 1e3 / (double)khz : 0.0;
-  for (int k = 0; k < 8; ++k) out8[k] = (k == 1 || k == 4 || k == 7) ? (double)h[k] : (double)h[k] * us;
+  for (int k = 0; k < 12; ++k) out12[k] = (k == 1 || k == 4 || k == 7 || k == 9) ? (double)h[k] : (double)h[k] * us;
 }
 
 bool fin_available(const cfem_ctx* c) { return c->world == 1 || c->p2p != nullptr; }

@@ -439,10 +439,17 @@ __device__ __forceinline__ bool t16_tile(const TileMeta& tm, const GhostSrc& gsr
     for (int e = tid + kTileNodes; e < ne; e += kTileNodes) xs[kTileNodes + e] = x[ext[e0 + e]];
   } else {
     const double* const mbox_shifted = gsrc.mbox - no;  // mbox_shifted[col] == mailbox[col - no]
+    const long long t0 = clock64();
     if (tid < ne) xs[kTileNodes + tid] = ecol >= no ? ghost_value(gsrc, mbox_shifted, ecol, no) : x[ecol];
     for (int e = tid + kTileNodes; e < ne; e += kTileNodes) {
       const int cc = ext[e0 + e];
       xs[kTileNodes + e] = cc >= no ? ghost_value(gsrc, mbox_shifted, cc, no) : x[cc];
+    }
+    if (gsrc.tim && tid == (ne - 1) % kTileNodes) {   // one sample per boundary tile: the poll of its last (ghost) column
+      const unsigned long long dt = (unsigned long long)(clock64() - t0);
+      atomicAdd(gsrc.tim + 8, dt);
+      atomicAdd(gsrc.tim + 9, 1ull);
+      atomicMax(gsrc.tim + 10, dt);
     }
   }
   EpPre q{0.0, 0.0, 0.0};
@@ -477,7 +484,18 @@ k_tile_t16(const GhostSrc gsrc, const int64_t no, const int32_t* __restrict__ ti
            const int32_t* __restrict__ status, const Fin fin) {
   int bid = blockIdx.x, nblk = gridDim.x;
   if (GHOST && gsrc.pushdev) {  // CTA 0 is the producer half of the halo exchange (p2p.cuh)
-    if (bid == 0) { pdl_wait(); pdl_launch(); ghost_push(gsrc, x, status && status[0]); return; }
+    if (bid == 0) {
+      pdl_wait();
+      pdl_launch();
+      // a capacity-limited grid gives one worker's slot to this CTA (launch_t16): the consumers of the per-CTA
+      // partials still read `grid` of them, so the slot of the missing worker holds the neutral element
+      if (EP::NACC >= 1 && nblk - 1 < ntiles) {
+        const Slots<(EP::NACC > 0 ? EP::NACC : 1)> sl = ep.parts();
+        if ((int)threadIdx.x < EP::NACC) sl.p[threadIdx.x][nblk - 1] = 0.0;
+      }
+      ghost_push(gsrc, x, status && status[0]);
+      return;
+    }
     --bid; --nblk;
   }
   extern __shared__ double t16_smem[];
@@ -577,8 +595,12 @@ static void launch_t16(cfem_ctx* c, const GhostSrc& gsrc, const Matrix& A, const
   const size_t smem = t16_smem_bytes(c);
   const int32_t* st = gated ? c->status : nullptr;
   const DevMesh& m = c->dm;
+  // With the producer CTA the grid must still be co-resident: one CTA more than the SMs hold would start only when
+  // the first worker retires and then run its whole schedule alone -- a tail as long as the push itself (measured:
+  // +5 us per launch on two GPUs, +11 us on eight).  A capacity-limited grid therefore gives up one worker instead.
+  const int total = gsrc.pushdev ? (grid < m.ntiles ? grid : grid + 1) : grid;
   if (gsrc.mbox)
-    launch_pdl(k_tile_t16<EP, true>, grid + (gsrc.pushdev ? 1 : 0), kTileNodes, smem, c->stream, gsrc, m.no, m.tile_order,
+    launch_pdl(k_tile_t16<EP, true>, total, kTileNodes, smem, c->stream, gsrc, m.no, m.tile_order,
                m.n_interior, m.ntiles, m.tile_node, m.rowptr, m.lc16, m.tile_extptr, m.tile_ext, A.vals, x, ep, st, fin);
   else
     launch_pdl(k_tile_t16<EP, false>, grid, kTileNodes, smem, c->stream, gsrc, m.no, m.tile_order, m.n_interior, m.ntiles,

@@ -102,8 +102,10 @@ int cfem_comm_stats(const cfem_ctx* ctx, int64_t* halo_exchanges, int64_t* allre
 /* Wait accounting of the peer-memory data plane since the last reset, measured on the device (no profiler):
  * out[0..2] halo waits: total us over all waiting CTAs, number of waits, longest single wait (us);
  * out[3..5] the cross-rank part of in-kernel all-reduces: total us, count, longest;
- * out[6..7] time the first worker CTA of the persistent solver spent in grid barriers: total us, count. */
-int cfem_comm_timers(cfem_ctx* ctx, double out[8], int reset);
+ * out[6..7] time the first worker CTA of the persistent solver spent in grid barriers: total us, count;
+ * out[8..10] halo-word polls of the staged tile kernels (Chebyshev chain, stand-alone SpMV): per boundary tile the
+ *            wait of the thread that polls the tile's last ghost column: total us, count, longest (us). */
+int cfem_comm_timers(cfem_ctx* ctx, double out[12], int reset);
 void cfem_destroy(cfem_ctx* ctx);
 int cfem_synchronize(cfem_ctx* ctx);
 
