@@ -856,6 +856,9 @@ static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps,
       res = res0 = partials_norm(c, normpart, np);
     }
     bool converged = !defer0 && res < p->newton_atol;
+    // CFEM_STEP_SYNC=1: poll the linear solve before queuing what follows it (two round trips per Newton iteration)
+    static const bool step_sync = getenv("CFEM_STEP_SYNC") && std::string(getenv("CFEM_STEP_SYNC")) == "1";
+    const bool async_solve = defer0 && !step_sync && p->solver == CFEM_SOLVER_BICGSTAB && bicgstab_async_available(c);
     int it = 0;
     while (!converged && it < p->newton_max_it) {
       if (it > 0 || !fused_fj) launch_cn_jacobian(c, p->flux, p->dt, c->uh, c->eps, J);
@@ -870,6 +873,33 @@ static int step_scalar_impl(cfem_ctx* c, const cfem_step_params* p, int n_steps,
       // from it keeps those rows out of the iteration (zero residual, decoupled), so uh - dx lands on g to the bit
       // like the reference's LU does.
       launch_copy_indexed(c, dx, F, c->d_bc_nodes, c->nbc);
+      if (async_solve) {
+        // ONE host round trip per Newton iteration: the solve, the update, the ghost refresh and the next residual are
+        // queued back to back; the verdict of the solve and ||F|| are read together.  (A failed solve has then already
+        // touched uh -- the step throws, and the fields of a failed step are undefined anyway.)
+        bicgstab_persist_begin(c, J, F, dx, p->lin_rtol, 0.0, p->lin_max_it);
+        if (use_guess && it == 0) {
+          if (!c->dx_guess) c->dx_guess = dalloc<double>(c, nn);
+          launch_copy(c, c->dx_guess, dx, nn);
+        }
+        // dolfinx takes no Newton step when the initial residual already meets atol: the device skips the update then
+        if (it == 0) launch_sub_unless_below(c, c->uh, dx, c->dm.no, c->scalars + 24, p->newton_atol * p->newton_atol);
+        else launch_sub(c, c->uh, dx, c->dm.no);
+        halo_exchange(c, c->uh);
+        np = launch_cn_residual(c, p->flux, p->dt, c->uh, c->u_n, c->eps, c->g, fluxn, F, normpart);
+        res = partials_norm(c, normpart, np);          // the round trip
+        const SolveResult rk = bicgstab_persist_end(c);
+        if (it == 0) {
+          res0 = sqrt(c->h_pinned[32]);
+          if (res0 < p->newton_atol) { res = res0; converged = true; break; }
+        }
+        if (!rk.converged) CFEM_THROW(-3, "step_scalar: Krylov solve did not converge (relres " + std::to_string(rk.relres) + ")");
+        st.krylov_iterations += rk.iters;
+        if (use_guess && it == 0) c->dx_guess_valid = true;
+        ++it;
+        converged = (res / res0 < p->newton_rtol) || (res < p->newton_atol);
+        continue;
+      }
       SolveResult rk = run_solver(c, p->solver, J, F, dx, p->lin_rtol, 0.0, p->lin_max_it, &c->krylov_predict);
       if (defer0 && it == 0) {
         CUDA_OK(cudaStreamSynchronize(c->stream));   // the solver's own poll has already drained the stream

@@ -634,6 +634,19 @@ void persist_comm_advance(cfem_ctx* c, int64_t halo_exchanges, int64_t allreduce
   c->allreduces += allreduces;
 }
 
+void persist_seq_reserve(cfem_ctx* c, int64_t halo_exchanges, int64_t allreduces) {
+  if (c->world == 1 || !c->p2p) return;
+  P2P* pp = (P2P*)c->p2p;
+  pp->halo_seq += (unsigned long long)halo_exchanges;
+  pp->red_seq += (unsigned long long)allreduces;
+}
+
+void persist_comm_count(cfem_ctx* c, int64_t halo_exchanges, int64_t allreduces) {
+  if (c->world == 1 || !c->p2p) return;
+  c->halo_exchanges += halo_exchanges;
+  c->allreduces += allreduces;
+}
+
 // cycles -> microseconds with the device's nominal SM clock; reset: start a new accounting interval
 void comm_timers(cfem_ctx* c, double* out12, bool reset) {
   for (int k = 0; k < 12; ++k) out12[k] = 0.0;

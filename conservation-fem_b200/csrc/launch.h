@@ -99,6 +99,12 @@ bool bicgstab_persist_available(cfem_ctx* c);
 void launch_bicg_persist(cfem_ctx* c, const Matrix& A, const double* rhat, double* x, double* r, double* p, double* v,
                          double* t, double rtol2, double atol2, int max_it);
 void persist_plan_free(cfem_ctx* c);
+bool bicgstab_async_available(cfem_ctx* c);
+void bicgstab_persist_begin(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol, int max_it);
+SolveResult bicgstab_persist_end(cfem_ctx* c);   // after a stream synchronisation that follows _begin
+void persist_seq_reserve(cfem_ctx* c, int64_t halo_exchanges, int64_t allreduces);   // protocol sequence numbers only
+void persist_comm_count(cfem_ctx* c, int64_t halo_exchanges, int64_t allreduces);    // statistics only
+void launch_sub_unless_below(cfem_ctx* c, double* x, const double* dx, int64_t n, const double* norm2, double thresh2);
 bool cheb_persist_available(cfem_ctx* c);
 void launch_cheb_persist(cfem_ctx* c, const Matrix& A, const double* b, double* x_in, double* x_other, double* d,
                          bool first, int iters, double rho0, double sigma1, double theta, double delta);

@@ -172,6 +172,18 @@ void launch_copy_indexed(cfem_ctx* c, double* dst, const double* src, const int3
   ProfScope ps(c, PROF_MISC);
   k_copy_indexed<<<vec_grid(c, n), kBlock, 0, c->stream>>>(dst, src, idx, n); LAUNCHED(c);
 }
+// x -= dx unless *norm2 < thresh2 (a device-side "the Newton iteration was not needed": the host learns it later)
+__global__ void k_sub_unless(double* __restrict__ x, const double* __restrict__ dx, int64_t n,
+                             const double* __restrict__ norm2, double thresh2) {
+  pdl_wait();
+  pdl_launch();
+  if (*norm2 < thresh2) return;
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) x[i] -= dx[i];
+}
+void launch_sub_unless_below(cfem_ctx* c, double* x, const double* dx, int64_t n, const double* norm2, double thresh2) {
+  ProfScope ps(c, PROF_MISC);
+  launch_pdl(k_sub_unless, vec_grid(c, n), kBlock, 0, c->stream, x, dx, n, norm2, thresh2); LAUNCHED(c);
+}
 void launch_sub(cfem_ctx* c, double* x, const double* dx, int64_t n) {
   ProfScope ps(c, PROF_MISC);
   launch_pdl(k_sub, vec_grid(c, n), kBlock, 0, c->stream, x, dx, n); LAUNCHED(c);
@@ -1427,10 +1439,47 @@ static SolveResult bicgstab_persist(cfem_ctx* c, const Matrix& A, const double* 
   { ProfScope ps(c, PROF_SOLVER);   // one launch = the whole BiCGStab loop (its own category of the breakdown)
     launch_bicg_persist(c, A, rhat, x, r, p, v, t, rtol2, atol2, max_it); }
   poll_done(c, res);
-  persist_comm_advance(c, 2 * (int64_t)res.iters, 3 * (int64_t)res.iters);
+  persist_comm_advance(c, 2 * (int64_t)res.iters, 3 * (int64_t)res.iters + (res.iters & 1));   // kernel pads to even
   // the ghost entries of x are NOT refreshed: the callers use the owned part (a Newton update, an exported result)
   // or exchange the vector they form from it
   if (predict) *predict = res.iters > 0 ? res.iters : 1;
+  return res;
+}
+
+// ---- asynchronous form: launch the solve and return; the caller queues the kernels that consume x, synchronises
+// the stream ONCE (for whatever it needs next) and then collects the verdict.  One host round trip per Newton
+// iteration instead of two -- each one drains the stream and, distributed, exposes the host latency of the slowest
+// rank to all of them.  The exchange sequence numbers the solve may use are reserved up front (even blocks, so the
+// slot parity of the next exchange is the one it would have had; see the end of k_bicg_persist).
+bool bicgstab_async_available(cfem_ctx* c) {
+  static const bool want5 = getenv("CFEM_BICGSTAB") && std::string(getenv("CFEM_BICGSTAB")) == "5k";
+  return !want5 && use_t16() && fin_available(c) && bicgstab_persist_available(c);
+}
+
+void bicgstab_persist_begin(cfem_ctx* c, const Matrix& A, const double* b, double* x, double rtol, double atol, int max_it) {
+  l2_prefer(c, A);
+  const int64_t n = c->dm.no;
+  double *r = c->wk[0], *rhat = c->wk[1], *p = c->wk[2], *v = c->wk[3], *t = c->wk[5];
+  const double rtol2 = rtol * rtol, atol2 = atol * atol;
+  spmv_dots<0>(c, A, x, v, nullptr, nullptr, nullptr, nullptr, false);
+  { ProfScope ps(c, PROF_KRYLOV_VEC);
+    launch_pdl(k_bm_init, vec_grid(c, n), kBlock, 0, c->stream, n, b, v, A.dinv, r, rhat, p, c->partials, c->scalars, c->status, rtol2, atol2, make_fin(c));
+    LAUNCHED(c); }
+  { ProfScope ps(c, PROF_SOLVER);
+    launch_bicg_persist(c, A, rhat, x, r, p, v, t, rtol2, atol2, max_it); }
+  CUDA_OK(cudaMemcpyAsync(c->h_status, c->status, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + S_RELRES, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  const int64_t halo = 2 * (int64_t)max_it, red = 3 * (int64_t)max_it + ((3 * (int64_t)max_it) & 1);
+  persist_seq_reserve(c, halo, red);
+}
+
+SolveResult bicgstab_persist_end(cfem_ctx* c) {
+  SolveResult res{0, 0.0, false};
+  if (c->h_status[3]) CFEM_THROW(-5, "a grid barrier of the persistent solver timed out");
+  res.iters = c->h_status[1];
+  res.relres = c->h_pinned[0];
+  res.converged = c->h_status[0] == 1;
+  persist_comm_count(c, 2 * (int64_t)res.iters, 3 * (int64_t)res.iters + (res.iters & 1));
   return res;
 }
 

@@ -345,6 +345,17 @@ k_bicg_persist(const BicgArgs a) {
     rho = rho_new;
     if (verdict != 0 || *(volatile int32_t*)(a.status + 3)) break;
   }
+  // Distributed: leave an EVEN number of cross-rank reductions behind (three per iteration; one empty reduction more
+  // after an odd iteration count).  The word slots of the all-reduce alternate with the parity of its sequence
+  // number, so the host can then reserve an even block of sequence numbers for the solve and queue the kernels that
+  // follow it -- without first learning the iteration count from the device (linalg.cu: bicgstab_persist_begin).
+  // The halo exchanges come in pairs (p, s) anyway.
+  if (a.dev && ((rseq - a.red_seq0) & 1ull) && !*(volatile int32_t*)(a.status + 3)) {
+    if (!comm_cta && tid == 0) pPQ[wid] = 0.0;
+    Slots<1> sl;
+    sl.p[0] = pPQ;
+    grid_reduce<1>(a, nblk, nwork, sl, ++rseq, out, sums, gen);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
