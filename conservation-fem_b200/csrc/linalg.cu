@@ -1439,7 +1439,7 @@ static SolveResult bicgstab_persist(cfem_ctx* c, const Matrix& A, const double* 
   { ProfScope ps(c, PROF_SOLVER);   // one launch = the whole BiCGStab loop (its own category of the breakdown)
     launch_bicg_persist(c, A, rhat, x, r, p, v, t, rtol2, atol2, max_it); }
   poll_done(c, res);
-  persist_comm_advance(c, 2 * (int64_t)res.iters, 3 * (int64_t)res.iters + (res.iters & 1));   // kernel pads to even
+  persist_comm_advance(c, 2 * (int64_t)res.iters, 2 * (int64_t)res.iters);   // per iteration: p and s halos, two reductions
   // the ghost entries of x are NOT refreshed: the callers use the owned part (a Newton update, an exported result)
   // or exchange the vector they form from it
   if (predict) *predict = res.iters > 0 ? res.iters : 1;
@@ -1469,8 +1469,7 @@ void bicgstab_persist_begin(cfem_ctx* c, const Matrix& A, const double* b, doubl
     launch_bicg_persist(c, A, rhat, x, r, p, v, t, rtol2, atol2, max_it); }
   CUDA_OK(cudaMemcpyAsync(c->h_status, c->status, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->h_pinned, c->scalars + S_RELRES, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  const int64_t halo = 2 * (int64_t)max_it, red = 3 * (int64_t)max_it + ((3 * (int64_t)max_it) & 1);
-  persist_seq_reserve(c, halo, red);
+  persist_seq_reserve(c, 2 * (int64_t)max_it, 2 * (int64_t)max_it);
 }
 
 SolveResult bicgstab_persist_end(cfem_ctx* c) {
@@ -1479,7 +1478,7 @@ SolveResult bicgstab_persist_end(cfem_ctx* c) {
   res.iters = c->h_status[1];
   res.relres = c->h_pinned[0];
   res.converged = c->h_status[0] == 1;
-  persist_comm_count(c, 2 * (int64_t)res.iters, 3 * (int64_t)res.iters + (res.iters & 1));
+  persist_comm_count(c, 2 * (int64_t)res.iters, 2 * (int64_t)res.iters);
   return res;
 }
 

@@ -11,8 +11,12 @@
 //       no barrier separates the update from the product);  t = D^-1 A s
 //                                                      partials (t,s) (t,t) (rhat,t) (rhat,s)
 //                                                                                  --- barrier + reduce: omega, rho', beta
-//   P4  x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v)
-//                                                      partial ||r||^2             --- barrier + reduce: verdict
+//   P4  x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v)   --- barrier (no reduction)
+//
+// ||r||^2 = (s,s) - 2 omega (t,s) + omega^2 (t,t) comes out of the second reduction, so the verdict on an iteration
+// is known BEFORE its update: the last iteration updates x only, and the third barrier carries no reduction -- two
+// cross-rank all-reduces per iteration in a distributed context instead of three.  (The recurrence loses digits only
+// when ||r|| << ||s||, i.e. relative error ~ 1e-16 ||s||^2 / ||r||^2; r = s - omega t takes a factor 2-5 off s.)
 //
 // A CTA owns the same tiles (rows) in every phase, so a row's own-entries are always produced and consumed by the
 // same thread; values of OTHER CTAs' rows (the external columns of a tile) are read with ld.global.cg after the
@@ -151,7 +155,8 @@ __device__ __forceinline__ void grid_reduce(const BicgArgs& a, const int nblk, c
 }
 
 // One SpMV-type phase over this CTA's tiles.  MODE 0: x = p, y = v, acc[0] += rhat.y.  MODE 1: x = r - alpha v,
-// y = t, acc = {(t,s), (t,t), (rhat,t), (rhat,s)}.
+// y = t, acc = {(t,s), (t,t), (rhat,t), (rhat,s), (s,s)}.
+__device__ __forceinline__ void grid_sync(unsigned int* bar, int32_t* status, int* error, const int nblk, unsigned int& gen);
 template <int MODE, bool GHOST>
 __device__ __forceinline__ void spmv_phase(const BicgArgs& a, const int wid, const int nwork, const double alpha,
                                            const unsigned long long hseq, double* prod, double* xs, int32_t* rp,
@@ -224,6 +229,7 @@ __device__ __forceinline__ void spmv_phase(const BicgArgs& a, const int wid, con
         acc[1] += s * s;
         acc[2] += rh * s;
         acc[3] += rh * xown;
+        acc[4] += xown * xown;
       }
     }
     __syncthreads();
@@ -238,7 +244,7 @@ k_bicg_persist(const BicgArgs a) {
   double* const xs = ps_smem + kTileNnzCap;   // [kTileNodes + ext_cap]
   __shared__ int32_t rp[kTileNodes + 1];
   __shared__ double red[9];
-  __shared__ double sums[4];
+  __shared__ double sums[5];
   const int tid = threadIdx.x;
   const int nblk = gridDim.x;
   const bool comm_cta = GHOST && blockIdx.x == 0;       // pushes halo values, owns no tile
@@ -257,12 +263,11 @@ k_bicg_persist(const BicgArgs a) {
   double* const out = a.scalars + PS_D0;
   double* const pPQ = a.part + (size_t)PP_PQ * kMaxPartials;
   double* const pA = a.part + (size_t)PP_A * kMaxPartials;
-  double* const pRR = a.part + (size_t)PP_RR * kMaxPartials;
 
   for (int it = 0; it < a.max_it; ++it) {
     // ------------------------------------------------ P1: v = D^-1 A p
     ++hseq;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (comm_cta) {
       const double* p = a.p;
       if (a.dev) push_ll(a.dev, hseq, [p](int node) { return __ldcg(p + node); });
@@ -284,28 +289,35 @@ k_bicg_persist(const BicgArgs a) {
       const double *r = a.r, *v = a.v;
       if (a.dev) push_ll(a.dev, hseq, [r, v, alpha](int node) { return __ldcg(r + node) - alpha * __ldcg(v + node); });
     } else {
-      acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+      acc[0] = acc[1] = acc[2] = acc[3] = acc[4] = 0.0;
       spmv_phase<1, GHOST>(a, wid, nwork, alpha, hseq, prod, xs, rp, smeta, acc);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 5; ++k) {
         const double sk = block_sum(acc[k], red);
         if (tid == 0) pA[(size_t)k * kMaxPartials + wid] = sk;
       }
     }
     {
-      Slots<4> sl;
+      Slots<5> sl;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) sl.p[k] = pA + (size_t)k * kMaxPartials;
-      grid_reduce<4>(a, nblk, nwork, sl, ++rseq, out, sums, gen);
+      for (int k = 0; k < 5; ++k) sl.p[k] = pA + (size_t)k * kMaxPartials;
+      grid_reduce<5>(a, nblk, nwork, sl, ++rseq, out, sums, gen);
     }
-    const double ts = sums[0], tt = sums[1], rt = sums[2], rs = sums[3];
+    const double ts = sums[0], tt = sums[1], rt = sums[2], rs = sums[3], ss = sums[4];
     const double omega = tt > 0.0 ? ts / tt : 0.0;
     const double rho_new = rs - omega * rt;   // (rhat, s - omega t)
     // omega == 0 only when s vanished (the alpha half-step solved the system): then r = s = 0 below and the verdict
     // is "converged"; beta must not turn that into 0 * inf
     const double beta = (omega != 0.0 && rho != 0.0) ? (rho_new / rho) * (alpha / omega) : 0.0;
-    // ------------------------------------------------ P4: x, r, p on this CTA's rows
-    double rr = 0.0;
+    // ||s - omega t||^2 from the dots at hand (never negative in exact arithmetic; clamp the rounding)
+    double grr = ss - 2.0 * omega * ts + omega * omega * tt;
+    if (grr < 0.0) grr = 0.0;
+    int verdict = 0;
+    if (!(grr == grr)) verdict = 2;
+    else if (grr <= a.rtol2 * bb || grr <= a.atol2) verdict = 1;
+    else if (!(beta == beta)) verdict = 2;   // breakdown: the next direction is not finite
+    if (it + 1 >= a.max_it && verdict == 0) verdict = -1;   // out of iterations: finish this update, report "not converged"
+    // ------------------------------------------------ P4: x (always); r, p unless this was the last iteration
     if (!comm_cta) {
       for (int kk = 0; kk < nrounds; ++kk) {
         const TileMeta tm = nrounds <= kMetaRounds ? smeta[kk]
@@ -314,48 +326,32 @@ k_bicg_persist(const BicgArgs a) {
         const int n0 = tm.n0, nrows = tm.nrows;
         if (tid < nrows) {
           const int row = n0 + tid;
-          const double vi = __ldcg(a.v + row), pi = __ldcg(a.p + row), ti = __ldcg(a.t + row);
+          const double vi = __ldcg(a.v + row), pi = __ldcg(a.p + row);
           const double si = __ldcg(a.r + row) - alpha * vi;
           a.x[row] = __ldcg(a.x + row) + alpha * pi + omega * si;
-          const double ri = si - omega * ti;
-          a.r[row] = ri;
-          a.p[row] = ri + beta * (pi - omega * vi);
-          rr += ri * ri;
+          if (verdict == 0) {
+            const double ri = si - omega * __ldcg(a.t + row);
+            a.r[row] = ri;
+            a.p[row] = ri + beta * (pi - omega * vi);
+          }
         }
       }
-      rr = block_sum(rr, red);
-      if (tid == 0) pRR[wid] = rr;
     }
-    {
-      Slots<1> sl;
-      sl.p[0] = pRR;
-      grid_reduce<1>(a, nblk, nwork, sl, ++rseq, out, sums, gen);
-    }
-    const double grr = sums[0];
-    int verdict = 0;
-    if (!(grr == grr)) verdict = 2;
-    else if (grr <= a.rtol2 * bb || grr <= a.atol2) verdict = 1;
-    else if (!(beta == beta)) verdict = 2;   // breakdown: the next direction is not finite
     if (blockIdx.x == 0 && tid == 0) {
       a.scalars[PS_RR] = grr;
       a.scalars[PS_RELRES] = bb > 0.0 ? sqrt(grr / bb) : sqrt(grr);
       a.status[1] = it + 1;
-      a.status[0] = verdict;
+      a.status[0] = verdict < 0 ? 0 : verdict;
     }
     rho = rho_new;
     if (verdict != 0 || *(volatile int32_t*)(a.status + 3)) break;
+    // next product reads p of other CTAs' rows: a plain grid barrier (nothing to reduce, nothing crosses the ranks)
+    grid_sync(a.bar, a.status, a.error, nblk, gen);
   }
-  // Distributed: leave an EVEN number of cross-rank reductions behind (three per iteration; one empty reduction more
-  // after an odd iteration count).  The word slots of the all-reduce alternate with the parity of its sequence
-  // number, so the host can then reserve an even block of sequence numbers for the solve and queue the kernels that
-  // follow it -- without first learning the iteration count from the device (linalg.cu: bicgstab_persist_begin).
-  // The halo exchanges come in pairs (p, s) anyway.
-  if (a.dev && ((rseq - a.red_seq0) & 1ull) && !*(volatile int32_t*)(a.status + 3)) {
-    if (!comm_cta && tid == 0) pPQ[wid] = 0.0;
-    Slots<1> sl;
-    sl.p[0] = pPQ;
-    grid_reduce<1>(a, nblk, nwork, sl, ++rseq, out, sums, gen);
-  }
+  // Two cross-rank reductions and two halo exchanges per iteration: the exchange sequence numbers a solve uses are
+  // even whatever its iteration count, so the host can reserve an even block of them and queue the kernels that
+  // follow the solve without first learning the count (linalg.cu: bicgstab_persist_begin) -- the word slots of the
+  // protocols alternate with the parity of the sequence number.
 }
 
 // ---------------------------------------------------------------------------------------------------------------
