@@ -460,3 +460,21 @@ def test_errors_are_loud():
         Context((x, np.array([[0, 1, 2]], dtype=np.int32)))
     with pytest.raises(CfemError):  # out of range vertex
         Context((x[:3], np.array([[0, 1, 7]], dtype=np.int32)))
+
+
+def test_measurement_hooks():
+    """cfem_time_kernel whole-solve ids, cfem_profile_gaps: shapes and sanity (values are machine dependent)."""
+    from cfem_b200 import _lib as L
+
+    x, c = meshes.rectangle(48, 48)
+    ctx = Context((x, c))
+    GS.solve_burgers(ctx, dt=1e-3, num_steps=2)            # leaves an assembled system matrix behind
+    ms_m, by_m = ctx.time_kernel(L.KERNEL_CHEB_ITER, "burgers", reps=2)
+    ms_k, by_k = ctx.time_kernel(L.KERNEL_KRYLOV_ITER, "burgers", reps=2)
+    assert ms_m > 0 and ms_k > 0 and by_m > 0 and by_k > 0
+    ctx.profile_begin(20000)
+    GS.solve_burgers(ctx, dt=1e-3, num_steps=2)
+    gaps = ctx.profile_gaps()
+    prof = ctx.profile_end()
+    assert set(gaps) == set(prof) == set(ctx.PROFILE_CATEGORIES)
+    assert all(v >= 0.0 for v in gaps.values()) and prof["solver"]["launches"] >= 2
