@@ -9,8 +9,8 @@
 //   P1  v = D^-1 A p                                   partial (rhat,v)            --- barrier + reduce: alpha
 //   P3  s = r - alpha v formed while STAGING (own rows and the tile's external columns, so s is never stored and
 //       no barrier separates the update from the product);  t = D^-1 A s
-//                                                      partials (t,s) (t,t) (rhat,t) (rhat,s)
-//                                                                                  --- barrier + reduce: omega, rho', beta
+//                                                      partials (t,s) (t,t) (rhat,t) (rhat,s) (s,s)
+//                                                                                  --- barrier + reduce: omega, rho', beta, ||r||^2
 //   P4  x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v)   --- barrier (no reduction)
 //
 // ||r||^2 = (s,s) - 2 omega (t,s) + omega^2 (t,t) comes out of the second reduction, so the verdict on an iteration
